@@ -1,0 +1,290 @@
+// extern "C" entry points of libldpc_b200.so (see include/ldpc_b200.h).
+//
+// Host-pointer entry points stream the batch through two slots (copy-in of chunk
+// i+1 overlaps the decode of chunk i and the copy-out of chunk i-1); device-pointer
+// entry points just enqueue the kernel.  All workspaces are per host thread, so a
+// code handle can be shared by any number of threads.
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+#include "ldpc_internal.h"
+
+using namespace ldpc;
+
+namespace {
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    unsigned long long *queue = nullptr;   // frame queue head
+    unsigned long long *counters = nullptr;
+    double *y = nullptr, *soft = nullptr;
+    uint8_t *bits = nullptr, *ok = nullptr;
+    int32_t *iters = nullptr;
+    size_t cap_frames = 0, cap_n = 0;
+    bool has_soft = false;
+};
+
+struct ThreadCtx {
+    std::map<int, Slot[2]> per_device;
+};
+
+thread_local ThreadCtx g_ctx;
+
+int slot_init(Slot &s) {
+    if (s.stream) return LDPC_OK;
+    LDPC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    LDPC_CUDA(cudaMalloc((void **) &s.queue, sizeof(unsigned long long)));
+    LDPC_CUDA(cudaMalloc((void **) &s.counters, sizeof(unsigned long long) * LDPC_CNT_COUNT));
+    return LDPC_OK;
+}
+
+int slot_reserve(Slot &s, size_t frames, size_t n, bool soft) {
+    if (frames <= s.cap_frames && n <= s.cap_n && (!soft || s.has_soft)) return LDPC_OK;
+    LDPC_CUDA(cudaStreamSynchronize(s.stream));
+    cudaFree(s.y); cudaFree(s.soft); cudaFree(s.bits); cudaFree(s.ok); cudaFree(s.iters);
+    s.y = s.soft = nullptr; s.bits = s.ok = nullptr; s.iters = nullptr;
+    s.cap_frames = std::max(frames, s.cap_frames);
+    s.cap_n = std::max(n, s.cap_n);
+    s.has_soft = soft || s.has_soft;
+    LDPC_CUDA(cudaMalloc((void **) &s.y, sizeof(double) * s.cap_frames * s.cap_n));
+    if (s.has_soft) LDPC_CUDA(cudaMalloc((void **) &s.soft, sizeof(double) * s.cap_frames * s.cap_n));
+    LDPC_CUDA(cudaMalloc((void **) &s.bits, s.cap_frames * s.cap_n));
+    LDPC_CUDA(cudaMalloc((void **) &s.ok, s.cap_frames));
+    LDPC_CUDA(cudaMalloc((void **) &s.iters, sizeof(int32_t) * s.cap_frames));
+    return LDPC_OK;
+}
+
+struct DecodeCfg {
+    int algo;
+    double snr, alpha, mu, eps_stop;
+    int max_iter, early_exit;
+};
+
+int enqueue_decode(const ldpc_code *c, const DecodeCfg &cfg, const FrameIO &io, int64_t frames,
+                   unsigned long long *queue, cudaStream_t stream) {
+    const double var = llr_variance(cfg.snr);
+    LDPC_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream));
+    if (cfg.algo == LDPC_ALGO_BP) return launch_bp(c, io, frames, var, cfg.max_iter, cfg.early_exit, queue, stream);
+    return launch_qpadmm(c, io, frames, var, cfg.alpha, cfg.mu, cfg.max_iter, cfg.eps_stop, queue, stream);
+}
+
+int check_common(const ldpc_code *c, const void *y, int64_t frames, const void *bits, const void *ok,
+                 const void *iters, int max_iter) {
+    if (!c) return fail(LDPC_E_INVALID, "code is NULL");
+    if (frames < 0) return fail(LDPC_E_INVALID, "frames < 0");
+    if (frames > 0 && (!y || !bits || !ok || !iters)) return fail(LDPC_E_INVALID, "NULL buffer");
+    if (max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
+    return LDPC_OK;
+}
+
+int decode_device(const ldpc_code *c, const DecodeCfg &cfg, const double *d_y, int64_t frames, uint8_t *d_bits,
+                  uint8_t *d_ok, int32_t *d_iters, double *d_soft, cudaStream_t stream) {
+    LDPC_CUDA(cudaSetDevice(c->device));
+    if (frames == 0) return LDPC_OK;
+    int st;
+    FrameIO io;
+    io.y = d_y; io.bits = d_bits; io.ok = d_ok; io.iters = d_iters; io.soft = d_soft;
+    // the frame-queue head is stream-ordered scratch of this launch
+    unsigned long long *queue = nullptr;
+    LDPC_CUDA(cudaMallocAsync((void **) &queue, sizeof(unsigned long long), stream));
+    st = enqueue_decode(c, cfg, io, frames, queue, stream);
+    cudaFreeAsync(queue, stream);
+    return st;
+}
+
+int decode_host(const ldpc_code *c, const DecodeCfg &cfg, const double *y, int64_t frames, uint8_t *bits,
+                uint8_t *ok, int32_t *iters, double *soft) {
+    LDPC_CUDA(cudaSetDevice(c->device));
+    if (frames == 0) return LDPC_OK;
+    const size_t n = c->n;
+    Slot *slots = g_ctx.per_device[c->device];
+    // chunk: <= 256 MiB of y per slot, and at least a few waves of CTAs
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(frames, (256ll << 20) / (int64_t) (n * sizeof(double))));
+    if (frames > chunk && frames < 2 * chunk) chunk = (frames + 1) / 2;
+    int st;
+    for (int s = 0; s < 2; ++s) {
+        if ((st = slot_init(slots[s]))) return st;
+        if (s == 0 || frames > chunk)
+            if ((st = slot_reserve(slots[s], (size_t) chunk, n, soft != nullptr))) return st;
+    }
+    int which = 0;
+    for (int64_t begin = 0; begin < frames; begin += chunk, which ^= 1) {
+        Slot &s = slots[which];
+        const int64_t cnt = std::min(chunk, frames - begin);
+        LDPC_CUDA(cudaMemcpyAsync(s.y, y + begin * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, s.stream));
+        FrameIO io;
+        io.y = s.y; io.bits = s.bits; io.ok = s.ok; io.iters = s.iters; io.soft = soft ? s.soft : nullptr;
+        if ((st = enqueue_decode(c, cfg, io, cnt, s.queue, s.stream))) return st;
+        LDPC_CUDA(cudaMemcpyAsync(bits + begin * n, s.bits, cnt * n, cudaMemcpyDeviceToHost, s.stream));
+        LDPC_CUDA(cudaMemcpyAsync(ok + begin, s.ok, cnt, cudaMemcpyDeviceToHost, s.stream));
+        LDPC_CUDA(cudaMemcpyAsync(iters + begin, s.iters, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (soft)
+            LDPC_CUDA(cudaMemcpyAsync(soft + begin * n, s.soft, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost,
+                                      s.stream));
+    }
+    LDPC_CUDA(cudaStreamSynchronize(slots[0].stream));
+    if (frames > chunk) LDPC_CUDA(cudaStreamSynchronize(slots[1].stream));
+    return LDPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldpc_bp_decode(const ldpc_code_t *c, const double *y, int64_t frames, double snr, int32_t max_iter,
+                   int32_t early_exit, uint8_t *bits, uint8_t *ok, int32_t *iters, double *post_llr) {
+    int st = check_common(c, y, frames, bits, ok, iters, max_iter);
+    if (st) return st;
+    DecodeCfg cfg{LDPC_ALGO_BP, snr, 0, 0, 0, max_iter, early_exit};
+    return decode_host(c, cfg, y, frames, bits, ok, iters, post_llr);
+}
+
+int ldpc_bp_decode_device(const ldpc_code_t *c, const double *d_y, int64_t frames, double snr, int32_t max_iter,
+                          int32_t early_exit, uint8_t *d_bits, uint8_t *d_ok, int32_t *d_iters,
+                          double *d_post_llr, void *stream) {
+    int st = check_common(c, d_y, frames, d_bits, d_ok, d_iters, max_iter);
+    if (st) return st;
+    DecodeCfg cfg{LDPC_ALGO_BP, snr, 0, 0, 0, max_iter, early_exit};
+    return decode_device(c, cfg, d_y, frames, d_bits, d_ok, d_iters, d_post_llr, (cudaStream_t) stream);
+}
+
+int ldpc_qpadmm_decode(const ldpc_code_t *c, const double *y, int64_t frames, double snr, double alpha, double mu,
+                       int32_t max_iter, double eps_stop, uint8_t *bits, uint8_t *ok, int32_t *iters,
+                       double *v_out) {
+    int st = check_common(c, y, frames, bits, ok, iters, max_iter);
+    if (st) return st;
+    DecodeCfg cfg{LDPC_ALGO_QPADMM, snr, alpha, mu, eps_stop, max_iter, 1};
+    return decode_host(c, cfg, y, frames, bits, ok, iters, v_out);
+}
+
+int ldpc_qpadmm_decode_device(const ldpc_code_t *c, const double *d_y, int64_t frames, double snr, double alpha,
+                              double mu, int32_t max_iter, double eps_stop, uint8_t *d_bits, uint8_t *d_ok,
+                              int32_t *d_iters, double *d_v_out, void *stream) {
+    int st = check_common(c, d_y, frames, d_bits, d_ok, d_iters, max_iter);
+    if (st) return st;
+    DecodeCfg cfg{LDPC_ALGO_QPADMM, snr, alpha, mu, eps_stop, max_iter, 1};
+    return decode_device(c, cfg, d_y, frames, d_bits, d_ok, d_iters, d_v_out, (cudaStream_t) stream);
+}
+
+int ldpc_channel_generate(const ldpc_code_t *c, uint64_t seed, uint64_t frame_begin, int64_t frames, double snr,
+                          const uint8_t *codewords, double *y) {
+    if (!c || frames < 0 || (frames > 0 && !y)) return fail(LDPC_E_INVALID, "bad argument");
+    if (frames == 0) return LDPC_OK;
+    LDPC_CUDA(cudaSetDevice(c->device));
+    const size_t n = c->n;
+    double *d_y = nullptr;
+    uint8_t *d_cw = nullptr;
+    LDPC_CUDA(cudaMalloc((void **) &d_y, sizeof(double) * frames * n));
+    int st = LDPC_OK;
+    if (codewords) {
+        cudaError_t e = cudaMalloc((void **) &d_cw, frames * n);
+        if (e == cudaSuccess) e = cudaMemcpy(d_cw, codewords, frames * n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) st = cuda_fail(e, "codeword upload", __FILE__, __LINE__);
+    }
+    if (!st) st = launch_channel(c, seed, frame_begin, frames, std::sqrt(llr_variance(snr)), d_cw, d_y, 0);
+    if (!st) {
+        cudaError_t e = cudaMemcpy(y, d_y, sizeof(double) * frames * n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) st = cuda_fail(e, "y download", __FILE__, __LINE__);
+    }
+    cudaFree(d_y);
+    cudaFree(d_cw);
+    return st;
+}
+
+int ldpc_channel_generate_device(const ldpc_code_t *c, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                                 double snr, const uint8_t *d_codewords, double *d_y, void *stream) {
+    if (!c || frames < 0 || (frames > 0 && !d_y)) return fail(LDPC_E_INVALID, "bad argument");
+    LDPC_CUDA(cudaSetDevice(c->device));
+    return launch_channel(c, seed, frame_begin, frames, std::sqrt(llr_variance(snr)), d_codewords, d_y,
+                          (cudaStream_t) stream);
+}
+
+int ldpc_generator_codewords(const ldpc_code_t *c, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                             uint8_t *codewords) {
+    if (!c || frames < 0 || (frames > 0 && !codewords)) return fail(LDPC_E_INVALID, "bad argument");
+    if (frames == 0) return LDPC_OK;
+    LDPC_CUDA(cudaSetDevice(c->device));
+    uint8_t *d = nullptr;
+    LDPC_CUDA(cudaMalloc((void **) &d, frames * (size_t) c->n));
+    int st = launch_generator_codewords(c, seed, frame_begin, frames, d, 0);
+    if (!st) {
+        cudaError_t e = cudaMemcpy(codewords, d, frames * (size_t) c->n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) st = cuda_fail(e, "codeword download", __FILE__, __LINE__);
+    }
+    cudaFree(d);
+    return st;
+}
+
+int ldpc_experiment_run(const ldpc_code_t *c, const ldpc_algo_cfg_t *cfg, double snr, uint64_t seed,
+                        uint64_t frame_begin, uint64_t frame_count, int32_t codeword_source, const uint8_t *words,
+                        uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT], double *gpu_seconds) {
+    if (!c || !cfg || !counters) return fail(LDPC_E_INVALID, "NULL argument");
+    if (cfg->algo != LDPC_ALGO_BP && cfg->algo != LDPC_ALGO_QPADMM) return fail(LDPC_E_INVALID, "unknown algo");
+    if (cfg->max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
+    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
+        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
+    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
+        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
+    if (codeword_source < LDPC_CW_ZERO || codeword_source > LDPC_CW_GENERATOR)
+        return fail(LDPC_E_INVALID, "unknown codeword source");
+    LDPC_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = 0;
+    if (gpu_seconds) *gpu_seconds = 0.0;
+    if (frame_count == 0) return LDPC_OK;
+
+    DecodeCfg dc{cfg->algo, snr, cfg->alpha, cfg->mu, cfg->eps_stop, cfg->max_iter, cfg->early_exit};
+    Slot &s = g_ctx.per_device[c->device][0];
+    int st = slot_init(s);
+    if (st) return st;
+    uint8_t *d_words = nullptr;
+    if (codeword_source == LDPC_CW_TABLE) {
+        LDPC_CUDA(cudaMalloc((void **) &d_words, n_words * (size_t) c->n));
+        cudaError_t e = cudaMemcpyAsync(d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { cudaFree(d_words); return cuda_fail(e, "codeword table upload", __FILE__, __LINE__); }
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * LDPC_CNT_COUNT, s.stream);
+    FrameIO io;
+    io.experiment = 1; io.seed = seed; io.frame_begin = frame_begin; io.cw_source = codeword_source;
+    io.words = d_words; io.n_words = n_words; io.counters = s.counters;
+    cudaEventRecord(e0, s.stream);
+    st = enqueue_decode(c, dc, io, (int64_t) frame_count, s.queue, s.stream);
+    cudaEventRecord(e1, s.stream);
+    unsigned long long host_cnt[LDPC_CNT_COUNT];
+    if (!st) {
+        cudaError_t e = cudaMemcpyAsync(host_cnt, s.counters, sizeof(host_cnt), cudaMemcpyDeviceToHost, s.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "experiment", __FILE__, __LINE__);
+    }
+    if (!st) {
+        for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = host_cnt[i];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (gpu_seconds) *gpu_seconds = ms * 1e-3;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_words);
+    return st;
+}
+
+int ldpc_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(LDPC_E_INVALID, "ptr is NULL");
+    LDPC_CUDA(cudaMallocHost(ptr, bytes));
+    return LDPC_OK;
+}
+
+int ldpc_host_free(void *ptr) {
+    LDPC_CUDA(cudaFreeHost(ptr));
+    return LDPC_OK;
+}
+
+int ldpc_measure_fp64_peak(int device, double *gfma_per_s) {
+    if (!gfma_per_s) return fail(LDPC_E_INVALID, "NULL argument");
+    return measure_fp64_peak(device, gfma_per_s);
+}
+
+}  // extern "C"

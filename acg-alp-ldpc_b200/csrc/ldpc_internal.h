@@ -1,0 +1,118 @@
+// Internal definitions shared by the translation units of libldpc_b200.so.
+// Nothing here is part of the ABI (include/ldpc_b200.h is).
+#ifndef LDPC_B200_INTERNAL_H
+#define LDPC_B200_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ldpc_b200.h"
+
+namespace ldpc {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int status, const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define LDPC_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t err__ = (call);                                            \
+        if (err__ != cudaSuccess) return ::ldpc::cuda_fail(err__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- device tables ----------------------------------------------------------
+// BP works per EDGE.  Edges have two numberings: the CSR position e (check-major,
+// V->C messages live in this order) and the CSC position p (variable-major, C->V
+// messages live in this order), so both phases gather from contiguous runs.
+struct BpEdgeC {      // indexed by CSR position e: what the check-side update of edge e needs
+    uint16_t begin;   // first CSR position of e's check
+    uint16_t end;     // one past the last
+    uint16_t dst;     // CSC position the C->V message is written to
+    uint16_t pad;
+};
+struct BpEdgeV {      // indexed by CSC position p: what the variable-side update needs
+    uint16_t begin;   // first CSC position of p's variable
+    uint16_t end;
+    uint16_t var;     // variable index (for the channel LLR)
+    uint16_t dst;     // CSR position the V->C message is written to
+};
+
+// QP-ADMM works per BLOCK: one three-variable check of the chain decomposition
+// (qp_admm.h:34-57, 84-91) with its 4 inequality rows, or a degree-2 / degree-1
+// check (2 rows / 1 row, qp_admm.h:70-83).  Row q of a block has coefficient +1
+// for slot q and for every slot in row 3, else -1.
+struct AdmmBlock {
+    uint16_t var[3];  // the block's variables in ASCENDING index order (the residual is
+                      // accumulated in that order, qp_admm.h:144-151); absent -> n_var (a zero)
+    uint16_t meta;    // bits 0-1 / 2-3 / 4-5: slot of var[0] / var[1] / var[2]; bits 8-10: rows
+};
+
+struct DeviceTables {
+    // BP
+    BpEdgeC *bp_c = nullptr;
+    BpEdgeV *bp_v = nullptr;
+    uint16_t *col_ptr = nullptr;   // n+1, CSC offsets
+    uint16_t *row_ptr = nullptr;   // m+1
+    uint16_t *col_idx = nullptr;   // E, variable of CSR position e
+    // QP-ADMM
+    AdmmBlock *blocks = nullptr;   // n_blocks
+    uint16_t *blk_order = nullptr; // n_blocks: blocks grouped by slot pattern, so a warp runs one pattern
+    uint32_t *var_ptr = nullptr;   // n_var+1 offsets into inc
+    uint16_t *inc = nullptr;       // incidences (block << 2 | slot), block ascending per variable
+    uint16_t *var_order = nullptr; // n_var: variables sorted by degree (descending) for balance
+    uint8_t *var_e = nullptr;      // n_var: e_i = sum of squared coefficients of column i
+    // generator (optional): column j of G packed over k bits, k_words words per column
+    uint32_t *gen_cols = nullptr;
+};
+
+}  // namespace ldpc
+
+struct ldpc_code {
+    int device = 0;
+    int m = 0, n = 0, E = 0;
+    int max_row_deg = 0, max_col_deg = 0;
+    int n_blocks = 0, n_var = 0, n_rows = 0, nnz = 0, n_inc = 0, e_min = 0;
+    int k = 0, k_words = 0;
+    // host copies (also used by tests through ldpc_code_info)
+    std::vector<int> row_ptr, col_idx, col_ptr, csc_edge;
+    ldpc::DeviceTables d;
+};
+
+namespace ldpc {
+
+// kernels / launchers (bp_kernel.cu, qpadmm_kernel.cu, channel_kernel.cu)
+struct FrameIO {
+    // decode mode: inputs/outputs per frame (device pointers; outputs may be null)
+    const double *y = nullptr;
+    uint8_t *bits = nullptr;
+    uint8_t *ok = nullptr;
+    int32_t *iters = nullptr;
+    double *soft = nullptr;  // BP: posterior LLR, QP-ADMM: v[0..n)
+    // experiment mode: y is generated on device
+    int experiment = 0;
+    uint64_t seed = 0, frame_begin = 0;
+    int cw_source = LDPC_CW_ZERO;
+    const uint8_t *words = nullptr;
+    uint64_t n_words = 0;
+    unsigned long long *counters = nullptr;  // LDPC_CNT_COUNT device words
+};
+
+int launch_bp(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
+              int early_exit, unsigned long long *queue, cudaStream_t stream);
+int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
+                  double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
+int launch_channel(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames, double sigma,
+                   const uint8_t *d_codewords, double *d_y, cudaStream_t stream);
+int launch_generator_codewords(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                               uint8_t *d_codewords, cudaStream_t stream);
+int measure_fp64_peak(int device, double *gfma_per_s);
+
+// sigma^2 exactly as utils/channel.h:12 computes it on the host
+double llr_variance(double snr);
+
+}  // namespace ldpc
+
+#endif

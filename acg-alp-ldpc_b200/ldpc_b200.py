@@ -1,0 +1,229 @@
+"""ctypes binding of libldpc_b200.so (the C ABI in include/ldpc_b200.h).
+
+This is the Python face of the product, used by tests/, bench.py and
+__graft_entry__.py.  It mirrors the reference's decoder objects:
+
+    BeliefPropagationDecoder(max_iter)                      algo/bp.h:208-222
+    QPADMMDecoder(alpha, mu, max_iter=2000, eps_stop=1e-5)  algo/qp_admm.h:180-194
+
+with ``decode(code, y, snr)`` taking a batch of channel words (frames x n raw
+samples, not LLRs) and a compiled ``Code`` instead of the dense H of every call.
+There is no CPU fallback: a missing library or missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
+
+CNT_NAMES = ["total", "correct", "pseudo", "decoder_fail", "bit_errors", "sum_hamming", "sum_hamming_ok",
+             "sum_hamming_wrong", "sum_iters", "frames_with_bits"]
+ALGO_BP, ALGO_QPADMM = 0, 1
+CW_ZERO, CW_TABLE, CW_GENERATOR = 0, 1, 2
+
+
+class LdpcError(RuntimeError):
+    pass
+
+
+class CodeInfo(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("m", "n", "edges", "max_row_deg", "max_col_deg", "admm_blocks",
+                                          "admm_n_var", "admm_rows", "admm_nnz", "admm_e_min", "k", "device")]
+
+
+class AlgoCfg(C.Structure):
+    _fields_ = [("algo", C.c_int32), ("max_iter", C.c_int32), ("early_exit", C.c_int32), ("reserved", C.c_int32),
+                ("alpha", C.c_double), ("mu", C.c_double), ("eps_stop", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the library once; raise (never fall back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LdpcError("%s is missing: run `python acg-alp-ldpc_b200/build.py` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, u64, i32, dbl = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_double
+    L.ldpc_last_error.restype = C.c_char_p
+    L.ldpc_abi_version.restype = C.c_int
+    L.ldpc_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.ldpc_code_create.argtypes = [i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
+    L.ldpc_code_create_dense.argtypes = [i32, i32, vp, C.c_int, C.POINTER(vp)]
+    L.ldpc_code_destroy.argtypes = [vp]
+    L.ldpc_code_destroy.restype = None
+    L.ldpc_code_info.argtypes = [vp, C.POINTER(CodeInfo)]
+    L.ldpc_code_set_generator.argtypes = [vp, i32, vp]
+    L.ldpc_bp_decode.argtypes = [vp, vp, i64, dbl, i32, i32, vp, vp, vp, vp]
+    L.ldpc_bp_decode_device.argtypes = [vp, vp, i64, dbl, i32, i32, vp, vp, vp, vp, vp]
+    L.ldpc_qpadmm_decode.argtypes = [vp, vp, i64, dbl, dbl, dbl, i32, dbl, vp, vp, vp, vp]
+    L.ldpc_qpadmm_decode_device.argtypes = [vp, vp, i64, dbl, dbl, dbl, i32, dbl, vp, vp, vp, vp, vp]
+    L.ldpc_channel_generate.argtypes = [vp, u64, u64, i64, dbl, vp, vp]
+    L.ldpc_channel_generate_device.argtypes = [vp, u64, u64, i64, dbl, vp, vp, vp]
+    L.ldpc_generator_codewords.argtypes = [vp, u64, u64, i64, vp]
+    L.ldpc_experiment_run.argtypes = [vp, C.POINTER(AlgoCfg), dbl, u64, u64, u64, i32, vp, u64, vp,
+                                      C.POINTER(dbl)]
+    L.ldpc_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.ldpc_host_free.argtypes = [vp]
+    L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        raise LdpcError("ldpc_b200 error %d: %s" % (status, lib().ldpc_last_error().decode()))
+
+
+def device_count():
+    n = C.c_int()
+    _check(lib().ldpc_device_count(C.byref(n)))
+    return n.value
+
+
+def measure_fp64_peak(device=0):
+    out = C.c_double()
+    _check(lib().ldpc_measure_fp64_peak(device, C.byref(out)))
+    return out.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Code:
+    """A parity-check matrix compiled and uploaded once (replaces the per-frame
+    graph builds of algo/bp.h:136-153 and algo/qp_admm.h:13-102)."""
+
+    def __init__(self, H=None, csr=None, shape=None, device=0):
+        L = lib()
+        self._h = C.c_void_p()
+        if H is not None:
+            H = np.ascontiguousarray(H, np.uint8)
+            m, n = H.shape
+            _check(L.ldpc_code_create_dense(m, n, H.ctypes.data, device, C.byref(self._h)))
+        else:
+            row_ptr, col_idx = (np.ascontiguousarray(a, np.int32) for a in csr)
+            m, n = shape
+            _check(L.ldpc_code_create(m, n, row_ptr.ctypes.data, col_idx.ctypes.data, device, C.byref(self._h)))
+        info = CodeInfo()
+        _check(L.ldpc_code_info(self._h, C.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in CodeInfo._fields_}
+        self.m, self.n = info.m, info.n
+
+    def close(self):
+        if self._h:
+            lib().ldpc_code_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_generator(self, G):
+        G = np.ascontiguousarray(G, np.uint8)
+        _check(lib().ldpc_code_set_generator(self._h, G.shape[0], G.ctypes.data))
+        self.info["k"] = G.shape[0]
+
+    # ---- channel ----------------------------------------------------------
+    def channel(self, seed, frame_begin, frames, snr, codewords=None):
+        y = np.empty((frames, self.n), np.float64)
+        cw = None if codewords is None else np.ascontiguousarray(codewords, np.uint8)
+        _check(lib().ldpc_channel_generate(self._h, seed, frame_begin, frames, snr, _ptr(cw), y.ctypes.data))
+        return y
+
+    def channel_device(self, seed, frame_begin, frames, snr, d_y, d_codewords=0, stream=0):
+        _check(lib().ldpc_channel_generate_device(self._h, seed, frame_begin, frames, snr, d_codewords or None, d_y,
+                                                  stream or None))
+
+    def generator_codewords(self, seed, frame_begin, frames):
+        out = np.empty((frames, self.n), np.uint8)
+        _check(lib().ldpc_generator_codewords(self._h, seed, frame_begin, frames, out.ctypes.data))
+        return out
+
+    # ---- decoders (host buffers) --------------------------------------------
+    def _out(self, frames, soft):
+        bits = np.empty((frames, self.n), np.uint8)
+        ok = np.empty(frames, np.uint8)
+        iters = np.empty(frames, np.int32)
+        s = np.empty((frames, self.n), np.float64) if soft else None
+        return bits, ok, iters, s
+
+    def bp_decode(self, y, snr, max_iter, early_exit=True, soft=True):
+        y = np.ascontiguousarray(y, np.float64).reshape(-1, self.n)
+        bits, ok, iters, post = self._out(y.shape[0], soft)
+        _check(lib().ldpc_bp_decode(self._h, y.ctypes.data, y.shape[0], snr, max_iter, int(early_exit),
+                                    bits.ctypes.data, ok.ctypes.data, iters.ctypes.data, _ptr(post)))
+        return bits, ok, iters, post
+
+    def qpadmm_decode(self, y, snr, alpha, mu, max_iter=2000, eps_stop=1e-5, soft=True):
+        y = np.ascontiguousarray(y, np.float64).reshape(-1, self.n)
+        bits, ok, iters, v = self._out(y.shape[0], soft)
+        _check(lib().ldpc_qpadmm_decode(self._h, y.ctypes.data, y.shape[0], snr, alpha, mu, max_iter, eps_stop,
+                                        bits.ctypes.data, ok.ctypes.data, iters.ctypes.data, _ptr(v)))
+        return bits, ok, iters, v
+
+    # ---- decoders (device pointers, asynchronous on `stream`) -----------------
+    def bp_decode_device(self, d_y, frames, snr, max_iter, early_exit, d_bits, d_ok, d_iters, d_post=0, stream=0):
+        _check(lib().ldpc_bp_decode_device(self._h, d_y, frames, snr, max_iter, int(early_exit), d_bits, d_ok,
+                                           d_iters, d_post or None, stream or None))
+
+    def qpadmm_decode_device(self, d_y, frames, snr, alpha, mu, max_iter, eps_stop, d_bits, d_ok, d_iters, d_v=0,
+                             stream=0):
+        _check(lib().ldpc_qpadmm_decode_device(self._h, d_y, frames, snr, alpha, mu, max_iter, eps_stop, d_bits,
+                                               d_ok, d_iters, d_v or None, stream or None))
+
+    # ---- Monte-Carlo point ----------------------------------------------------
+    def experiment(self, decoder, snr, seed, frame_begin, frame_count, source=CW_ZERO, words=None):
+        cfg = decoder.cfg()
+        cnt = np.zeros(len(CNT_NAMES), np.uint64)
+        secs = C.c_double()
+        w = None if words is None else np.ascontiguousarray(words, np.uint8)
+        _check(lib().ldpc_experiment_run(self._h, C.byref(cfg), snr, seed, frame_begin, frame_count, source,
+                                         _ptr(w), 0 if w is None else w.shape[0], cnt.ctypes.data,
+                                         C.byref(secs)))
+        res = dict(zip(CNT_NAMES, (int(x) for x in cnt)))
+        res["gpu_seconds"] = secs.value
+        return res
+
+
+class BeliefPropagationDecoder:
+    """algo/bp.h:208-222; early_exit=False is the fixed-iteration measurement mode."""
+
+    def __init__(self, max_iter, early_exit=True):
+        self.max_iter, self.early_exit = int(max_iter), bool(early_exit)
+
+    def name(self):
+        return "BP"
+
+    def cfg(self):
+        return AlgoCfg(ALGO_BP, self.max_iter, int(self.early_exit), 0, 0.0, 0.0, 0.0)
+
+    def decode(self, code, y, snr):
+        """-> (bits, ok): ok[f] False means the reference returns an EMPTY word (bp.h:198)."""
+        bits, ok, _, _ = code.bp_decode(y, snr, self.max_iter, self.early_exit, soft=False)
+        return bits, ok.astype(bool)
+
+
+class QPADMMDecoder:
+    """algo/qp_admm.h:180-194"""
+
+    def __init__(self, alpha, mu, max_iter=2000, eps_stop=1e-5):
+        self.alpha, self.mu, self.max_iter, self.eps_stop = float(alpha), float(mu), int(max_iter), float(eps_stop)
+
+    def name(self):
+        return "QP-ADMM"
+
+    def cfg(self):
+        return AlgoCfg(ALGO_QPADMM, self.max_iter, 1, 0, self.alpha, self.mu, self.eps_stop)
+
+    def decode(self, code, y, snr):
+        bits, ok, _, _ = code.qpadmm_decode(y, snr, self.alpha, self.mu, self.max_iter, self.eps_stop, soft=False)
+        return bits, ok.astype(bool)

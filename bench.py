@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the hot path: decoded frames/s at fixed iterations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): BP sum-product, 100 fixed iterations, on the
+H05 code (160 x 280), AWGN frames at -5 dB.  One "step" = one batch of
+--frames frames through the decode kernel; 1e7 frames per SNR point = 1e7/frames
+steps.  -5 dB is used because there the reference's BP (which cannot switch its
+syndrome exit off) also runs all 100 iterations on >= 99.8 % of frames, so the CPU
+arm does the same work on the same kind of input.  QP-ADMM (optimalH, 1000 fixed
+iterations, eps_stop = 0) is measured in the same run and reported under "qpadmm".
+
+One JSON line on stdout (rank 0).  Keys follow the driver's contract; the
+roofline is the FP64 pipe (messages never leave the SM, so HBM traffic is ~0.1 %
+of peak -- reported under roofline.hbm for completeness).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "acg-alp-ldpc_b200"))
+from tests.helpers import load_rows  # noqa: E402  (only the .rows parser)
+
+SEED = 239239239
+BP_SNR, BP_ITERS = -5.0, 100
+ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
+# algorithmic fp64 instructions per unit of work (DESIGN.md "rooflines"):
+BP_FP64_PER_EDGE_ITER = 48.0          # exp 15 + log-ratio 19 + leave-one-out products 9 + sums 3 + sign/abs 2
+ADMM_FP64_PER_BLOCK_ITER = 54.0       # 12 gather adds + 9 residual + 29 row updates + 3.6 v ops per block
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- reference arm
+
+def _ref_worker(args):
+    """one single-threaded process of the UNMODIFIED reference (race-free)"""
+    algo, code_name, frames, begin = args
+    from oracle.oracle import Oracle, Ref
+    ref, orc = Ref(), Oracle()
+    H = load_rows(code_name)
+    n = H.shape[1]
+    if algo == "bp":
+        y = orc.channel(SEED, begin, frames, n, BP_SNR)
+        t0 = time.perf_counter()
+        _, ok, secs = ref.bp_decode(H, y, BP_SNR, BP_ITERS)
+    else:
+        y = orc.channel(SEED, begin, frames, n, ADMM_SNR)
+        t0 = time.perf_counter()
+        _, ok, secs = ref.qpadmm_decode(H, y, ADMM_SNR, ADMM_ALPHA, ADMM_MU, ADMM_ITERS, 0.0)
+    return time.perf_counter() - t0, secs, frames
+
+
+def reference_sample(algo, code_name, frames_per_proc, procs, begin=0):
+    """frames/s of the reference's CPU decoder on `procs` host cores (wall clock over all processes)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    jobs = [(algo, code_name, frames_per_proc, begin + i * frames_per_proc) for i in range(procs)]
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    inner = max(r[0] for r in res)
+    return frames_per_proc * procs / inner, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import have_ref, build
+    build(ref=True)
+    cores = host_cores()
+    kind = "reference" if have_ref() else "port"
+    if not have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so was not built"}))
+        return
+    per_proc = max(2, int(round(args.ref_seconds / 0.07)))          # ~0.07 s per BP(100) frame per core
+    for _ in range(args.warmup):
+        reference_sample("bp", "H05", 2, cores)
+    t0 = time.perf_counter()
+    vals = []
+    for s in range(args.steps):
+        v, _ = reference_sample("bp", "H05", per_proc, cores, begin=s * per_proc * cores)
+        vals.append(v)
+    elapsed = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = "%d frames/step = %d procs x %d frames, BP(100) H05 @ %g dB, 1 thread per process" % (
+        per_proc * cores, cores, per_proc, BP_SNR)
+    print(json.dumps({
+        "impl": "reference", "metric": "decoded frames/sec (BP, fixed 100 iters)", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f80", "data": "synthetic",
+        "config": {"workload": "BP(100 iters) on H05 160x280, AWGN @ %g dB" % BP_SNR, "frames_per_step": per_proc * cores},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------- GPU arm
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import ldpc_b200 as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    hbm_peak, peak_kind, _ = peaks()
+    fp64_peak = L.measure_fp64_peak(local)            # G fp64 FMA instr/s, measured on this GPU
+
+    def bench_algo(algo, code_name, frames, steps, warmup):
+        H = load_rows(code_name)
+        m, n = H.shape
+        code = L.Code(H=H, device=local)
+        snr = BP_SNR if algo == "bp" else ADMM_SNR
+        # inputs resident in HBM: two alternating batches, each larger than L2 (126 MB) for BP
+        ys = []
+        for b in range(2):
+            y = torch.empty((frames, n), dtype=torch.float64, device=dev)
+            begin = (rank * 2 + b) * frames
+            code.channel_device(SEED, begin, frames, snr, y.data_ptr(), 0, sptr)
+            ys.append(y)
+        bits = torch.empty((frames, n), dtype=torch.uint8, device=dev)
+        ok = torch.empty(frames, dtype=torch.uint8, device=dev)
+        iters = torch.empty(frames, dtype=torch.int32, device=dev)
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+
+        def step_device(i):
+            y = ys[i & 1]
+            if algo == "bp":
+                code.bp_decode_device(y.data_ptr(), frames, snr, BP_ITERS, False, bits.data_ptr(), ok.data_ptr(),
+                                      iters.data_ptr(), 0, sptr)
+            else:
+                code.qpadmm_decode_device(y.data_ptr(), frames, snr, ADMM_ALPHA, ADMM_MU, ADMM_ITERS, 0.0,
+                                          bits.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, sptr)
+
+        for i in range(warmup):
+            step_device(i)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            step_device(i)
+        e1.record(stream)
+        # the path's only collective: error/iteration counters, once at the end
+        counts[0] = ok.sum()
+        counts[1] = iters.sum()
+        if world > 1:
+            dist.all_reduce(counts)
+        barrier()
+        t_host1 = time.perf_counter()
+        clocks = sampler.stop(t_host0, t_host1) if sampler else None
+        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        wall_ms = max_over_ranks(1e3 * (t_host1 - t_host0))
+        assert int(iters.min().item()) == (BP_ITERS if algo == "bp" else ADMM_ITERS), "fixed-iteration mode broken"
+
+        # end to end through the public host-buffer API: pinned y in, bits/ok/iters out, every step
+        e2e_frames = frames
+        y_pin = torch.empty((e2e_frames, n), dtype=torch.float64).pin_memory()
+        y_pin.copy_(ys[0].cpu())
+        b_pin = torch.empty((e2e_frames, n), dtype=torch.uint8).pin_memory()
+        ok_pin = torch.empty(e2e_frames, dtype=torch.uint8).pin_memory()
+        it_pin = torch.empty(e2e_frames, dtype=torch.int32).pin_memory()
+        lib = L.lib()
+
+        def step_e2e():
+            if algo == "bp":
+                st = lib.ldpc_bp_decode(code._h, y_pin.data_ptr(), e2e_frames, snr, BP_ITERS, 0, b_pin.data_ptr(),
+                                        ok_pin.data_ptr(), it_pin.data_ptr(), None)
+            else:
+                st = lib.ldpc_qpadmm_decode(code._h, y_pin.data_ptr(), e2e_frames, snr, ADMM_ALPHA, ADMM_MU,
+                                            ADMM_ITERS, 0.0, b_pin.data_ptr(), ok_pin.data_ptr(),
+                                            it_pin.data_ptr(), None)
+            assert st == 0, lib.ldpc_last_error()
+
+        e2e_steps = max(1, min(steps, 3))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+
+        info = code.info
+        units = info["edges"] if algo == "bp" else info["admm_blocks"]
+        per_unit = BP_FP64_PER_EDGE_ITER if algo == "bp" else ADMM_FP64_PER_BLOCK_ITER
+        n_iter = BP_ITERS if algo == "bp" else ADMM_ITERS
+        fps_gpu = frames * steps / (dev_ms * 1e-3)                      # this rank's kernel throughput
+        value = world * frames * steps / (dev_ms * 1e-3)
+        achieved = fps_gpu * n_iter * units * per_unit / 1e9            # G fp64 instr/s on one GPU
+        bytes_per_frame = n * 8 + n + 1 + 4
+        k = info["n"] - info["m"]
+        res = {
+            "value": value, "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
+            "info_gbit_per_s": value * k / 1e9,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "Gop/s (fp64 instr)",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "peak_source": "ldpc_measure_fp64_peak on this GPU (8 independent DFMA chains/thread)",
+                         "work_per_launch": "%d frames x %d iters x %d %s x %.0f fp64 instr" % (
+                             frames, n_iter, units, "edges" if algo == "bp" else "blocks", per_unit),
+                         "hbm": {"achieved": fps_gpu * bytes_per_frame / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": fps_gpu * bytes_per_frame / 1e9 / hbm_peak, "peak_kind": peak_kind}},
+            "e2e": {"value": world * e2e_frames * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": e2e_frames * n * 8, "d2h_bytes_per_step": e2e_frames * (n + 5)},
+            "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),
+        }
+        code.close()
+        return res
+
+    bp = bench_algo("bp", "H05", args.frames, args.steps, args.warmup)
+    admm = bench_algo("qpadmm", "optimalH", max(1024, args.frames // 8), args.steps, args.warmup)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import have_ref
+        if have_ref():
+            cores = host_cores()
+            per_proc = max(2, int(round(args.ref_seconds / 0.07)))
+            v, wall = reference_sample("bp", "H05", per_proc, cores)
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
+                   "sample": "%d procs x %d frames, unmodified reference BP(100) on H05 @ %g dB, 1 thread/process, "
+                             "%.1f s wall" % (cores, per_proc, BP_SNR, wall)}
+    if rank == 0:
+        line = {
+            "metric": "decoded frames/sec (BP, fixed 100 iters)", "value": bp["value"], "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": bp["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BP(100 fixed iters, syndrome exit off) on H05 160x280, AWGN @ %g dB, "
+                                   "%d frames/step/GPU (configs[1]: 1e7 frames/point = %d steps)" % (
+                                       BP_SNR, args.frames, -(-10 ** 7 // args.frames)),
+                       "frames_per_step_per_gpu": args.frames, "parallelism": "frames sharded over %d GPU(s)" % world,
+                       "l2_policy": "inputs larger than L2: two alternating %d MB batches" % (
+                           args.frames * 280 * 8 >> 20)},
+            "info_gbit_per_s": bp["info_gbit_per_s"], "roofline": bp["roofline"], "e2e": bp["e2e"],
+            "clocks": bp["clocks"], "gpu_launches": args.steps, "cpu_baseline": cpu,
+            "qpadmm": {"metric": "decoded frames/sec (QP-ADMM, fixed 1000 iters, eps_stop=0)",
+                       "config": {"workload": "QP-ADMM(alpha=%g, mu=%g, 1000 iters) on optimalH 160x280 @ %g dB" % (
+                           ADMM_ALPHA, ADMM_MU, ADMM_SNR), "frames_per_step_per_gpu": admm["frames_per_step"]},
+                       "value": admm["value"], "ms_per_step": admm["ms_per_step"],
+                       "info_gbit_per_s": admm["info_gbit_per_s"], "roofline": admm["roofline"], "e2e": admm["e2e"],
+                       "clocks": admm["clocks"]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 18, help="frames per step per GPU (BP); QP-ADMM uses 1/8")
+    ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per core of one reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/* ldpc_b200.h -- C ABI of the B200 (sm_100a) batched LDPC decoding engine.
+ *
+ * This is the drop-in boundary for ONE hot path of GreatDrake/acg-alp-ldpc:
+ * belief-propagation and QP-ADMM decoding of many independent AWGN frames.
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ * Each entry point names the reference interface it replaces (file:line in the
+ * reference tree).  The reference-side bindings (the C++ Decoder adapters and
+ * the ctypes stub) are in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int status: LDPC_OK (0) or a negative LDPC_E_*;
+ *     ldpc_last_error() gives the message of the calling thread's last failure.
+ *     There is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with LDPC_E_CUDA.
+ *   - a code handle is immutable after creation and may be used from many host
+ *     threads at once (the reference calls Decoder::decode concurrently from up to
+ *     200 pthreads, experiment.h:128-130); per-call workspaces are internal.
+ *   - frames are rows: y is frames x n doubles (raw channel samples, NOT LLRs:
+ *     the LLR scaling 2*y/sigma^2 happens on the device exactly as
+ *     utils/channel.h:12-16 does it), bits is frames x n bytes (0/1).
+ *   - snr is Es/N0 in dB (utils/channel.h:12).
+ *   - "_device" variants take device pointers and a cudaStream_t (as void*) and
+ *     are asynchronous; the plain variants take host pointers, copy in and out,
+ *     and return when the results are in the caller's buffers.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_ABI_VERSION 1
+
+enum {
+    LDPC_OK = 0,
+    LDPC_E_INVALID = -1,   /* bad argument */
+    LDPC_E_CUDA = -2,      /* CUDA runtime / no device */
+    LDPC_E_NOMEM = -3,
+    LDPC_E_UNSUPPORTED = -4 /* code too large for the on-chip layout */
+};
+
+typedef struct ldpc_code ldpc_code_t;
+
+/* Shape of a compiled code. */
+typedef struct {
+    int32_t m, n;        /* checks, variables */
+    int32_t edges;       /* ones in H */
+    int32_t max_row_deg, max_col_deg;
+    int32_t admm_blocks; /* three-variable checks (+ degree-1/2 special blocks) */
+    int32_t admm_n_var;  /* n + auxiliary variables */
+    int32_t admm_rows;   /* inequality rows R */
+    int32_t admm_nnz;
+    int32_t admm_e_min;  /* min_i sum_j A_ji^2, used by the feasibility test qp_admm.h:108-114 */
+    int32_t k;           /* generator rows attached with ldpc_code_set_generator, else 0 */
+    int32_t device;
+} ldpc_code_info_t;
+
+/* Counter block of one Monte-Carlo point.  The first fields are the reference's
+ * ExperimentResult / HammingDistanceTracker (experiment.h:25-68) widened to
+ * 64 bit; bit_errors / sum_iters / frames_with_bits are extensions:
+ * bit errors are counted over frames that return n bits (QP-ADMM: all frames;
+ * BP: converged frames). */
+enum {
+    LDPC_CNT_TOTAL = 0,
+    LDPC_CNT_CORRECT,
+    LDPC_CNT_PSEUDO,
+    LDPC_CNT_DECODER_FAIL,
+    LDPC_CNT_BIT_ERRORS,
+    LDPC_CNT_SUM_HAMMING,
+    LDPC_CNT_SUM_HAMMING_OK,
+    LDPC_CNT_SUM_HAMMING_WRONG,
+    LDPC_CNT_SUM_ITERS,
+    LDPC_CNT_FRAMES_WITH_BITS,
+    LDPC_CNT_COUNT
+};
+
+enum { LDPC_ALGO_BP = 0, LDPC_ALGO_QPADMM = 1 };
+
+/* Where the transmitted codewords of an experiment come from. */
+enum {
+    LDPC_CW_ZERO = 0,      /* all-zero codeword */
+    LDPC_CW_TABLE = 1,     /* caller's table: frame f sends words[f % n_words] (experiment.h:86-93) */
+    LDPC_CW_GENERATOR = 2  /* c = u*G on device, u from Philox stream 0 (utils/channel.h:29-36) */
+};
+
+/* Decoder configuration: the constructor arguments of BeliefPropagationDecoder
+ * (algo/bp.h:210) and QPADMMDecoder (algo/qp_admm.h:182). */
+typedef struct {
+    int32_t algo;       /* LDPC_ALGO_* */
+    int32_t max_iter;
+    int32_t early_exit; /* 1 = reference behaviour (BP: syndrome exit bp.h:195-196).  0 = fixed-iteration
+                           measurement mode for BP (QP-ADMM uses eps_stop = 0 for that, as the reference can) */
+    int32_t reserved;
+    double alpha, mu, eps_stop; /* QP-ADMM only */
+} ldpc_algo_cfg_t;
+
+int ldpc_abi_version(void);
+const char *ldpc_last_error(void);
+int ldpc_device_count(int *count);
+
+/* ---- code handle: replaces the per-frame graph builds from_biadjacency_matrix
+ * (algo/bp.h:136-153) and ConstructADMMProblem (algo/qp_admm.h:13-102) by one
+ * compile + upload per H.  CSR: row_ptr[m+1], col_idx[edges], columns ascending
+ * within a row.  `device` is the CUDA ordinal the tables are uploaded to. */
+int ldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, int device,
+                     ldpc_code_t **out);
+/* Same from the reference's dense TMatrix layout (m x n bytes, row-major, nonzero = 1). */
+int ldpc_code_create_dense(int32_t m, int32_t n, const uint8_t *H, int device, ldpc_code_t **out);
+void ldpc_code_destroy(ldpc_code_t *code);
+int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info);
+/* Attach G (k x n dense bytes, e.g. GetOrtogonal(H).first, utils/codeword.h:97-128)
+ * for LDPC_CW_GENERATOR experiments.  Not thread-safe against running calls. */
+int ldpc_code_set_generator(ldpc_code_t *code, int32_t k, const uint8_t *G);
+
+/* ---- belief propagation: BeliefPropagationDecoder::decode (algo/bp.h:208-222),
+ * batched.  ok[f] = the decoder's bool; bits of frames with ok == 0 are zero
+ * (the reference returns an EMPTY codeword, bp.h:198).  iters[f] = iterations
+ * run.  post_llr (frames x n, may be NULL) = VNode::estimate() (bp.h:85-90) of
+ * the last iteration. */
+int ldpc_bp_decode(const ldpc_code_t *code, const double *y, int64_t frames, double snr, int32_t max_iter,
+                   int32_t early_exit, uint8_t *bits, uint8_t *ok, int32_t *iters, double *post_llr);
+int ldpc_bp_decode_device(const ldpc_code_t *code, const double *d_y, int64_t frames, double snr,
+                          int32_t max_iter, int32_t early_exit, uint8_t *d_bits, uint8_t *d_ok,
+                          int32_t *d_iters, double *d_post_llr, void *stream);
+
+/* ---- QP-ADMM: QPADMMDecoder::decode -> DecodeQPADMM (algo/qp_admm.h:104-194),
+ * batched, fp64, the reference's floating-point operation order.  ok[f] = 0
+ * only for the infeasible-parameter exit (min(e)*mu <= alpha, qp_admm.h:108-114;
+ * bits all zero, iters 0).  v_out (frames x n, may be NULL) = relaxed solution
+ * v[0..n) at exit. */
+int ldpc_qpadmm_decode(const ldpc_code_t *code, const double *y, int64_t frames, double snr, double alpha,
+                       double mu, int32_t max_iter, double eps_stop, uint8_t *bits, uint8_t *ok,
+                       int32_t *iters, double *v_out);
+int ldpc_qpadmm_decode_device(const ldpc_code_t *code, const double *d_y, int64_t frames, double snr,
+                              double alpha, double mu, int32_t max_iter, double eps_stop, uint8_t *d_bits,
+                              uint8_t *d_ok, int32_t *d_iters, double *d_v_out, void *stream);
+
+/* ---- channel: transmit() (utils/channel.h:19-26) from a counter-based
+ * Philox4x32-10 stream instead of mt19937 + std::normal_distribution.
+ * Global frame index f uses counter (f, block, stream); the CPU oracle replays
+ * the same y bit for bit.  codewords: NULL (all-zero) or frames x n bytes.
+ * y: frames x n doubles (host). */
+int ldpc_channel_generate(const ldpc_code_t *code, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                          double snr, const uint8_t *codewords, double *y);
+/* Same with device pointers (d_codewords may be NULL), asynchronous on `stream`. */
+int ldpc_channel_generate_device(const ldpc_code_t *code, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                                 double snr, const uint8_t *d_codewords, double *d_y, void *stream);
+/* The codewords an LDPC_CW_GENERATOR experiment transmits (frames x n bytes, host). */
+int ldpc_generator_codewords(const ldpc_code_t *code, uint64_t seed, uint64_t frame_begin, int64_t frames,
+                             uint8_t *codewords);
+
+/* ---- Monte-Carlo point: exp() + multithread_experiment() (experiment.h:80-139)
+ * for global frames [frame_begin, frame_begin + frame_count): device-side
+ * codeword selection, AWGN, decoding, verdict (experiment.h:109-118) and
+ * counting; only the counter block comes back.  words/n_words are used by
+ * LDPC_CW_TABLE (n_words x n bytes, host).  gpu_seconds (may be NULL) = device
+ * time of the decode kernels (CUDA events). */
+int ldpc_experiment_run(const ldpc_code_t *code, const ldpc_algo_cfg_t *cfg, double snr, uint64_t seed,
+                        uint64_t frame_begin, uint64_t frame_count, int32_t codeword_source,
+                        const uint8_t *words, uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT],
+                        double *gpu_seconds);
+
+/* ---- pinned host buffers for the host-pointer entry points (optional: any
+ * host memory works, pinned memory makes the copies asynchronous). */
+int ldpc_host_alloc(void **ptr, uint64_t bytes);
+int ldpc_host_free(void *ptr);
+
+/* ---- roofline support: measured issue rate of dependent-free fp64 FMAs on the
+ * device of `device` (G FMA instructions/s per thread-op, i.e. lanes x clock),
+ * used as the denominator of the FP64 roofline in bench.py. */
+int ldpc_measure_fp64_peak(int device, double *gfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

@@ -1,0 +1,240 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle
+on identical inputs, against the reference's golden vectors, and -- at sizes the
+oracle cannot follow -- through size-independent properties.
+
+Bars (BASELINE.json north_star):
+  * channel samples, QP-ADMM hard decisions / iteration counts / v: bit-exact
+  * BP: hard decisions, success flag and converging iteration identical per frame
+    (>= 99.99 % required; every mismatch is printed), posterior LLR within 1e-4 relative
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import dense_to_csr
+from tests.helpers import GOLDEN, load_rows, small_irregular_code, wilson_interval
+
+pytestmark = pytest.mark.gpu
+
+SEED = 239239239
+ADMM = {"optimalH": (1.2, 0.55), "H05": (1.95, 0.5), "reg_3_6_1008": (1.2, 0.55)}
+
+
+@pytest.fixture(scope="module")
+def codes(gpu_lib):
+    out = {}
+    for name in ("optimalH", "H05", "reg_3_6_1008"):
+        H = load_rows(name)
+        out[name] = (H, gpu_lib.Code(H=H), dense_to_csr(H))
+    return out
+
+
+def test_code_info_matches_survey_table(codes):
+    want = {"optimalH": (900, 580, 700, 2320, 6960, 4), "H05": (860, 540, 660, 2160, 6480, 4),
+            "reg_3_6_1008": (3024, 2016, 2520, 8064, 24192, 8)}
+    for name, (E, T, nv, R, nnz, emin) in want.items():
+        info = codes[name][1].info
+        assert (info["edges"], info["admm_blocks"], info["admm_n_var"], info["admm_rows"], info["admm_nnz"],
+                info["admm_e_min"]) == (E, T, nv, R, nnz, emin)
+
+
+def test_channel_bit_exact_with_oracle(codes, oracle):
+    for name in ("optimalH", "reg_3_6_1008"):
+        H, code, _ = codes[name]
+        n = H.shape[1]
+        rng = np.random.default_rng(1)
+        cw = rng.integers(0, 2, (64, n)).astype(np.uint8)      # any bits: the channel does not care
+        for snr, begin in ((-3.0, 0), (0.5, (1 << 33) + 12345)):
+            y_gpu = code.channel(SEED, begin, 64, snr, cw)
+            y_cpu = oracle.channel(SEED, begin, 64, n, snr, cw)
+            assert y_gpu.tobytes() == y_cpu.tobytes()
+        y0 = code.channel(SEED + 1, 7, 16, -1.0)
+        assert y0.tobytes() == oracle.channel(SEED + 1, 7, 16, n, -1.0).tobytes()
+
+
+@pytest.mark.parametrize("name,snrs,frames,max_iter", [
+    ("optimalH", (-4.0, -3.0, -1.0), 96, 1000),
+    ("H05", (-3.0, 0.0), 64, 1000),
+    ("reg_3_6_1008", (-2.0, 0.0), 24, 300),
+])
+def test_qpadmm_bit_exact(codes, oracle, name, snrs, frames, max_iter):
+    H, code, csr = codes[name]
+    m, n = H.shape
+    alpha, mu = ADMM[name]
+    for snr in snrs:
+        y = code.channel(SEED, 1000, frames, snr)
+        gb, gok, git, gv = code.qpadmm_decode(y, snr, alpha, mu, max_iter, 1e-5)
+        ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, max_iter, 1e-5)
+        bad = np.flatnonzero((gb != ob).any(1) | (git != oit) | (gok != ook))
+        for f in bad:
+            print("QP-ADMM mismatch %s snr=%g frame=%d iters gpu/cpu=%d/%d" % (name, snr, f, git[f], oit[f]))
+        assert len(bad) == 0
+        assert (gv == ov).all(), "v differs by up to %g" % np.abs(gv - ov).max()
+    # fixed-iteration mode (eps_stop = 0) runs every iteration
+    y = code.channel(SEED, 5, 8, 0.0)
+    gb, gok, git, gv = code.qpadmm_decode(y, 0.0, alpha, mu, 50, 0.0)
+    ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, 0.0, alpha, mu, 50, 0.0)
+    assert (git == 50).all() and (oit == 50).all() and (gv == ov).all() and (gb == ob).all()
+
+
+@pytest.mark.parametrize("name,snrs,frames", [
+    ("optimalH", (-4.0, -3.0, -2.0, 0.0), 128),
+    ("H05", (-3.0, -1.0), 96),
+    ("reg_3_6_1008", (-1.0, 1.0), 24),
+])
+def test_bp_matches_fp80_oracle(codes, oracle, name, snrs, frames):
+    H, code, csr = codes[name]
+    m, n = H.shape
+    total = mism = 0
+    for snr in snrs:
+        y = code.channel(SEED, 2000, frames, snr)
+        gb, gok, git, gpost = code.bp_decode(y, snr, 100)
+        ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, snr, 100)
+        bad = np.flatnonzero((gb != ob).any(1) | (gok != ook) | (git != oit))
+        for f in bad:
+            print("BP mismatch %s snr=%g frame=%d ok gpu/cpu=%d/%d iters=%d/%d" %
+                  (name, snr, f, gok[f], ook[f], git[f], oit[f]))
+        total += frames
+        mism += len(bad)
+        conv = (gok == 1) & (ook == 1)
+        rel = np.abs(gpost[conv] - opost[conv]) / np.maximum(np.abs(opost[conv]), 1e-300)
+        assert rel.size == 0 or rel.max() < 1e-4, "posterior LLR off by %g relative" % rel.max()
+        assert (gb[gok == 0] == 0).all()      # failed frames return no bits (bp.h:198)
+    assert mism == 0, "%d of %d frames differ" % (mism, total)
+
+
+def test_bp_fixed_iteration_mode(codes, oracle):
+    H, code, csr = codes["optimalH"]
+    m, n = H.shape
+    y = code.channel(SEED, 0, 32, -1.0)
+    gb, gok, git, gpost = code.bp_decode(y, -1.0, 20, early_exit=False)
+    ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, -1.0, 20, early_exit=False)
+    assert (git == 20).all() and (gok == ook).all() and (gb == ob).all()
+    ok = gok == 1
+    assert np.allclose(gpost[ok], opost[ok], rtol=1e-4, atol=0)
+
+
+@pytest.mark.parametrize("name", ["optimalH", "H05"])
+def test_reference_golden_vectors(codes, name):
+    """outputs of the unmodified reference on its own mt19937 channel words"""
+    g = np.load(os.path.join(GOLDEN, "ref_%s.npz" % name))
+    H, code, _ = codes[name]
+    alpha, mu = g["alpha_mu"]
+    for si, snr in enumerate(g["snrs"]):
+        y = g["y_%d" % si]
+        bits, ok, _, _ = code.bp_decode(y, float(snr), 100)
+        assert (ok == g["bp_ok_%d" % si]).all() and (bits == g["bp_bits_%d" % si]).all()
+        bits, ok, _, _ = code.qpadmm_decode(y, float(snr), alpha, mu, 1000, 1e-5)
+        assert (ok == g["admm_ok_%d" % si]).all() and (bits == g["admm_bits_%d" % si]).all()
+
+
+def test_edge_cases(gpu_lib, codes, oracle):
+    H, code, csr = codes["optimalH"]
+    m, n = H.shape
+    # empty batch, single frame, ragged batch sizes
+    b, ok, it, s = code.bp_decode(np.zeros((0, n)), 0.0, 10)
+    assert b.shape == (0, n) and ok.shape == (0,)
+    b, ok, it, s = code.qpadmm_decode(np.zeros((0, n)), 0.0, 1.2, 0.55, 10, 1e-5)
+    assert b.shape == (0, n)
+    for frames in (1, 3, 149, 1000):
+        y = code.channel(SEED, 99, frames, 0.0)
+        b, ok, it, _ = code.bp_decode(y, 0.0, 100)
+        assert ok.all() and (b == 0).all()           # all-zero codeword at 0 dB
+        b2, ok2, it2, _ = code.qpadmm_decode(y, 0.0, 1.2, 0.55, 2000, 1e-5)
+        assert ok2.all() and (b2 == 0).all()
+        if frames == 149:
+            ob, ook, oit, _ = oracle.bp_decode(csr, m, n, y[:20], 0.0, 100)
+            assert (oit == it[:20]).all()
+    # infeasible parameters: min(e) mu <= alpha -> {zeros, false}, qp_admm.h:108-114
+    y = code.channel(SEED, 0, 5, 0.0)
+    b, ok, it, v = code.qpadmm_decode(y, 0.0, 3.0, 0.5, 100, 1e-5)
+    assert (ok == 0).all() and (b == 0).all() and (it == 0).all() and (v == 0).all()
+    # max_iter = 0: BP fails at once, QP-ADMM returns the initial v = (q > 0)
+    b, ok, it, _ = code.bp_decode(y, 0.0, 0)
+    assert (ok == 0).all() and (b == 0).all() and (it == 0).all()
+    ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, 0.0, 1.2, 0.55, 0, 1e-5)
+    b, ok, it, v = code.qpadmm_decode(y, 0.0, 1.2, 0.55, 0, 1e-5)
+    assert (b == ob).all() and (ok == ook).all() and (it == 0).all()
+
+
+def test_irregular_code_special_blocks(gpu_lib, oracle):
+    """checks of degree 0/1/2 and isolated variables (qp_admm.h:67-83; bp.h handles them implicitly)"""
+    H = small_irregular_code()
+    m, n = H.shape
+    code = gpu_lib.Code(H=H)
+    csr = dense_to_csr(H)
+    rng = np.random.default_rng(3)
+    y = 1.0 + 0.8 * rng.standard_normal((40, n))
+    gb, gok, git, gv = code.qpadmm_decode(y, 1.0, -0.3, 0.6, 300, 1e-5)
+    ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, 1.0, -0.3, 0.6, 300, 1e-5)
+    assert (gb == ob).all() and (gok == ook).all() and (git == oit).all() and (gv == ov).all()
+    gb, gok, git, gv = code.qpadmm_decode(y, 1.0, 0.5, 0.6, 300, 1e-5)     # e_min = 0 -> infeasible
+    assert (gok == 0).all() and (gb == 0).all()
+    gb, gok, git, gpost = code.bp_decode(y, 1.0, 30)
+    ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, 1.0, 30)
+    assert (gb == ob).all() and (gok == ook).all() and (git == oit).all()
+    fin = np.isfinite(opost) & (ook == 1)[:, None]
+    assert np.allclose(gpost[fin], opost[fin], rtol=1e-4, atol=0)
+    assert (np.isinf(gpost) == np.isinf(opost))[ook == 1].all()           # degree-1 checks pin a bit: LLR = +inf
+
+
+def test_experiment_counters_match_oracle(gpu_lib, codes, oracle):
+    """device-side codeword + AWGN + decode + verdict + counting == the oracle's replay"""
+    H, code, csr = codes["optimalH"]
+    m, n = H.shape
+    g = np.load(os.path.join(GOLDEN, "ref_generator_optimalH.npz"))
+    G = np.unpackbits(g["G"], axis=1)[:, :n]
+    code.set_generator(G)
+    # the generated codewords themselves
+    cw_gpu = code.generator_codewords(SEED, 10, 16)
+    for f in range(16):
+        assert (cw_gpu[f] == oracle.encode(G, oracle.info_bits(SEED, 10 + f, G.shape[0]))).all()
+    bp = gpu_lib.BeliefPropagationDecoder(100)
+    admm = gpu_lib.QPADMMDecoder(1.2, 0.55, 1000, 1e-5)
+    keys = ["total", "correct", "pseudo", "decoder_fail", "bit_errors", "sum_hamming", "sum_hamming_ok",
+            "sum_hamming_wrong", "sum_iters", "frames_with_bits"]
+    for snr in (-3.0, -1.5):
+        for source, kw in ((gpu_lib.CW_GENERATOR, dict(G=G)), (gpu_lib.CW_ZERO, {}),
+                           (gpu_lib.CW_TABLE, dict(words=cw_gpu))):
+            for dec, algo in ((bp, "bp"), (admm, "qpadmm")):
+                got = code.experiment(dec, snr, SEED, 500, 60, source, kw.get("words"))
+                want = oracle.experiment(algo, csr, m, n, snr, dec.max_iter, SEED, 500, 60, alpha=1.2, mu=0.55,
+                                         eps_stop=1e-5, **kw)
+                assert {k: got[k] for k in keys} == want, (snr, source, algo)
+    # sharding invariance: counters over [0, 300) == sum over three disjoint shards (any GPU count)
+    whole = code.experiment(admm, -2.0, SEED, 0, 300, gpu_lib.CW_GENERATOR)
+    parts = [code.experiment(admm, -2.0, SEED, b, c, gpu_lib.CW_GENERATOR) for b, c in ((0, 100), (100, 37), (137, 163))]
+    for k in keys:
+        assert whole[k] == sum(p[k] for p in parts)
+
+
+def test_full_size_properties(gpu_lib, codes):
+    """sizes the CPU oracle cannot follow: round trips and statistics"""
+    H, code, _ = codes["optimalH"]
+    n = H.shape[1]
+    g = np.load(os.path.join(GOLDEN, "ref_generator_optimalH.npz"))
+    G = np.unpackbits(g["G"], axis=1)[:, :n]
+    code.set_generator(G)
+    bp = gpu_lib.BeliefPropagationDecoder(100)
+    admm = gpu_lib.QPADMMDecoder(1.2, 0.55, 10000, 1e-5)
+    # encode -> (almost noiseless) channel -> decode returns the transmitted word, every frame
+    for dec in (bp, admm):
+        r = code.experiment(dec, 6.0, SEED, 0, 200000, gpu_lib.CW_GENERATOR)
+        assert r["total"] == 200000 and r["correct"] == 200000 and r["bit_errors"] == 0 and r["pseudo"] == 0
+    # FER at -3 dB agrees with the race-free reference numbers (BP 529/1000, QP-ADMM 744/1000
+    # correct on mt19937 noise) within binomial confidence intervals
+    for dec, ref_correct in ((bp, 529), (admm, 744)):
+        r = code.experiment(dec, -3.0, SEED, 0, 20000, gpu_lib.CW_GENERATOR)
+        lo, hi = wilson_interval(ref_correct, 1000, z=3.3)
+        p = r["correct"] / r["total"]
+        assert lo <= p <= hi, (dec.name(), p, lo, hi)
+        # channel symmetry: the all-zero codeword sees the same FER
+        r0 = code.experiment(dec, -3.0, SEED + 1, 0, 20000, gpu_lib.CW_ZERO)
+        lo, hi = wilson_interval(r["correct"], r["total"], z=4.0)
+        assert lo - 0.01 <= r0["correct"] / r0["total"] <= hi + 0.01
+    # mean channel Hamming distance ~ n * Q(1/sigma)
+    from math import erfc, sqrt
+    sigma = sqrt(10 ** 0.3 / 2)
+    expect = n * 0.5 * erfc(1 / sigma / sqrt(2))
+    assert abs(r["sum_hamming"] / r["total"] - expect) < 0.2
