@@ -266,6 +266,7 @@ int orc_qpadmm_decode(int m, int n, const int *row_ptr, const int *col_idx, cons
         double *yl = (double *) calloc(R > 0 ? R : 1, sizeof(double));
         double *r = (double *) malloc(sizeof(double) * (R > 0 ? R : 1));
         double *inv_coef = (double *) malloc(sizeof(double) * n_var);
+        for (int i = 0; i < n_var; ++i) v[i] = q[i] > 0.0 ? 1.0 : 0.0;   /* :116-119, visible only if max_iter == 0 */
         for (int i = 0; i < n_var; ++i) {
             double A = (mu * e[i] - alpha) / 2;
             inv_coef[i] = -1.0 / (2 * A);

@@ -29,6 +29,10 @@ def test_decoders_frame_by_frame(oracle, ref, name, alpha, mu):
         rb, rok, _ = ref.qpadmm_decode(H, y, snr, alpha, mu, 600, 1e-5)
         ob, ook, _, _ = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, 600, 1e-5)
         assert (rok == ook).all() and (rb == ob).all()
+        for iters in (0, 1, 7):             # max_iter = 0 returns the initial v = (q > 0), qp_admm.h:116-119
+            rb, rok, _ = ref.qpadmm_decode(H, y[:6], snr, alpha, mu, iters, 1e-5)
+            ob, ook, oit, _ = oracle.qpadmm_decode(csr, m, n, y[:6], snr, alpha, mu, iters, 1e-5)
+            assert (rok == ook).all() and (rb == ob).all() and (oit == iters).all()
 
 
 def test_irregular_code_special_cases(oracle, ref):
