@@ -282,6 +282,13 @@ int ldpc_host_free(void *ptr) {
     return LDPC_OK;
 }
 
+int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *ev, const double *od, double *out_exp,
+                      double *out_log) {
+    if (count < 0 || (count > 0 && (!a || !ev || !od || !out_exp || !out_log))) return fail(LDPC_E_INVALID, "bad argument");
+    if (count == 0) return LDPC_OK;
+    return debug_bpmath(device, count, a, ev, od, out_exp, out_log);
+}
+
 int ldpc_measure_fp64_peak(int device, double *gfma_per_s) {
     if (!gfma_per_s) return fail(LDPC_E_INVALID, "NULL argument");
     return measure_fp64_peak(device, gfma_per_s);

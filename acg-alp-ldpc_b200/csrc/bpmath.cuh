@@ -1,0 +1,88 @@
+// fp64 transcendental kernels of the BP message update, written for instruction
+// count: the decoder is bound by the FP64 pipe (64 lanes/SM) and by issue slots,
+// so both functions are straight-line DFMA chains with a handful of integer ops,
+// no special-case branches and no libm calls.
+#ifndef LDPC_B200_BPMATH_CUH
+#define LDPC_B200_BPMATH_CUH
+
+namespace ldpc {
+
+// exp(-a) for a >= 0 (a = +inf allowed), relative error < 2 ulp.
+// a is clamped to 700 on its high word, so the result never underflows to a
+// denormal and no message magnitude downstream reaches infinity:
+//   k = rint(-a log2 e) through the 1.5*2^52 trick, r = -a - k ln2 (two-part ln2),
+//   degree-12 Taylor polynomial on |r| <= ln2/2, exponent patched in.
+__device__ __forceinline__ double exp_neg(double a) {
+    const int hi_a = min(__double2hiint(a), 0x4085e000);          // 700.0: an integer min on the high word
+    a = __hiloint2double(hi_a, __double2loint(a));
+    const double magic = 6755399441055744.0;                      // 1.5 * 2^52
+    double kf = __fma_rn(a, -1.4426950408889634, magic);
+    const int k = __double2loint(kf);
+    kf -= magic;
+    double r = __fma_rn(kf, -0x1.62e42fefa0000p-1, -a);           // ln2 high part (trailing bits zero)
+    r = __fma_rn(kf, -0x1.cf79abc9e3b3ap-40, r);                  // ln2 low part
+    double p = 0x1.1eed8eff8d898p-29;                             // 1/12!
+    p = __fma_rn(p, r, 0x1.ae64567f544e4p-26);                    // 1/11!
+    p = __fma_rn(p, r, 0x1.27e4fb7789f5cp-22);                    // 1/10!
+    p = __fma_rn(p, r, 0x1.71de3a556c734p-19);                    // 1/9!
+    p = __fma_rn(p, r, 0x1.a01a01a01a01ap-16);                    // 1/8!
+    p = __fma_rn(p, r, 0x1.a01a01a01a01ap-13);                    // 1/7!
+    p = __fma_rn(p, r, 0x1.6c16c16c16c17p-10);                    // 1/6!
+    p = __fma_rn(p, r, 0x1.1111111111111p-7);                     // 1/5!
+    p = __fma_rn(p, r, 0x1.5555555555555p-5);                     // 1/4!
+    p = __fma_rn(p, r, 0x1.5555555555555p-3);                     // 1/3!
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+__device__ __forceinline__ double rcp_fast(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));        // MUFU.RCP64H, ~2^-23
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+
+// log(ev / od) for ev >= od >= 0, ev in [1, 2^60): absolute error ~1e-14.
+// od is clamped to the smallest normal, so od == 0 (a degree-1 check, or every
+// other input saturated) gives ~log(ev) + 708 instead of +inf.
+//   ev = 2^ke me, od = 2^ko mo, me, mo in [1,2);  if me < mo: me *= 2, ke -= 1, so me/mo in [1,2)
+//   log(me/mo) = log(c) + 2 atanh(s),  c = sqrt(2) rounded,  s = (me - c mo)/(me + c mo),  |s| <= 0.1716
+__device__ __forceinline__ double log_ratio(double ev, double od) {
+    int hi_e = __double2hiint(ev);
+    int hi_o = max(__double2hiint(od), 0x00100000);
+    int d = (hi_e >> 20) - (hi_o >> 20);
+    hi_e = (hi_e & 0x000fffff) | 0x3ff00000;
+    hi_o = (hi_o & 0x000fffff) | 0x3ff00000;
+    double me = __hiloint2double(hi_e, __double2loint(ev));
+    const double mo = __hiloint2double(hi_o, __double2loint(od));
+    if (me < mo) {
+        me = __hiloint2double(hi_e + 0x00100000, __double2loint(ev));
+        d -= 1;
+    }
+    const double c = 1.4142135623730951;
+    const double num = __fma_rn(-c, mo, me);
+    const double den = __fma_rn(c, mo, me);
+    const double s = num * rcp_fast(den);
+    const double s2 = s * s;
+    double p = 0x1.af286bca1af28p-5;                              // 1/19
+    p = __fma_rn(p, s2, 0x1.e1e1e1e1e1e1ep-5);                    // 1/17
+    p = __fma_rn(p, s2, 0x1.1111111111111p-4);                    // 1/15
+    p = __fma_rn(p, s2, 0x1.3b13b13b13b14p-4);                    // 1/13
+    p = __fma_rn(p, s2, 0x1.745d1745d1746p-4);                    // 1/11
+    p = __fma_rn(p, s2, 0x1.c71c71c71c71cp-4);                    // 1/9
+    p = __fma_rn(p, s2, 0x1.2492492492492p-3);                    // 1/7
+    p = __fma_rn(p, s2, 0x1.999999999999ap-3);                    // 1/5
+    p = __fma_rn(p, s2, 0x1.5555555555555p-2);                    // 1/3
+    const double two_s = s + s;
+    const double u = __fma_rn(two_s, s2 * p, two_s);
+    // log(c) rounds to 0x1.62e42fefa39f0p-2 (c is sqrt(2) rounded to double; residual 2.4e-17)
+    return __fma_rn((double) d, 0x1.62e42fefa39efp-1, 0x1.62e42fefa39f0p-2 + u);
+}
+
+}  // namespace ldpc
+
+#endif

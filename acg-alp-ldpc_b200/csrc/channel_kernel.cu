@@ -2,6 +2,7 @@
 // issue-rate microbenchmark that provides the FP64 roofline denominator.
 #include <algorithm>
 
+#include "bpmath.cuh"
 #include "frame.cuh"
 
 namespace ldpc {
@@ -65,6 +66,32 @@ int launch_generator_codewords(const ldpc_code *c, uint64_t seed, uint64_t frame
     generator_kernel<<<grid, 256, 0, stream>>>(seed, frame_begin, frames, c->n, c->k, c->k_words, c->d.gen_cols,
                                                d_codewords);
     LDPC_CUDA(cudaGetLastError());
+    return LDPC_OK;
+}
+
+__global__ void bpmath_kernel(int count, const double *a, const double *ev, const double *od, double *out_exp,
+                              double *out_log) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        out_exp[i] = exp_neg(a[i]);
+        out_log[i] = log_ratio(ev[i], od[i]);
+    }
+}
+
+int debug_bpmath(int device, int count, const double *a, const double *ev, const double *od, double *out_exp,
+                 double *out_log) {
+    LDPC_CUDA(cudaSetDevice(device));
+    double *d = nullptr;
+    const size_t bytes = sizeof(double) * (size_t) count;
+    LDPC_CUDA(cudaMalloc((void **) &d, 5 * bytes));
+    LDPC_CUDA(cudaMemcpy(d, a, bytes, cudaMemcpyHostToDevice));
+    LDPC_CUDA(cudaMemcpy(d + count, ev, bytes, cudaMemcpyHostToDevice));
+    LDPC_CUDA(cudaMemcpy(d + 2 * (size_t) count, od, bytes, cudaMemcpyHostToDevice));
+    bpmath_kernel<<<148, 256>>>(count, d, d + count, d + 2 * (size_t) count, d + 3 * (size_t) count,
+                                d + 4 * (size_t) count);
+    LDPC_CUDA(cudaGetLastError());
+    LDPC_CUDA(cudaMemcpy(out_exp, d + 3 * (size_t) count, bytes, cudaMemcpyDeviceToHost));
+    LDPC_CUDA(cudaMemcpy(out_log, d + 4 * (size_t) count, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return LDPC_OK;
 }
 

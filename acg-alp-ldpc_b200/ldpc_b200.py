@@ -71,6 +71,7 @@ def lib():
     L.ldpc_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.ldpc_host_free.argtypes = [vp]
     L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
+    L.ldpc_debug_bpmath.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -90,6 +91,14 @@ def measure_fp64_peak(device=0):
     out = C.c_double()
     _check(lib().ldpc_measure_fp64_peak(device, C.byref(out)))
     return out.value
+
+
+def debug_bpmath(a, ev, od, device=0):
+    a, ev, od = (np.ascontiguousarray(x, np.float64) for x in (a, ev, od))
+    out_exp, out_log = np.empty_like(a), np.empty_like(a)
+    _check(lib().ldpc_debug_bpmath(device, a.size, a.ctypes.data, ev.ctypes.data, od.ctypes.data, out_exp.ctypes.data,
+                                   out_log.ctypes.data))
+    return out_exp, out_log
 
 
 def _ptr(a):

@@ -173,6 +173,12 @@ int ldpc_host_free(void *ptr);
  * used as the denominator of the FP64 roofline in bench.py. */
 int ldpc_measure_fp64_peak(int device, double *gfma_per_s);
 
+/* ---- testing hook: the two fp64 kernels of the BP message update evaluated element-wise on the
+ * device (host arrays of `count` doubles): out_exp[i] = exp(-a[i]) for a >= 0, out_log[i] =
+ * log(ev[i] / od[i]) for ev >= od >= 0. */
+int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *ev, const double *od,
+                      double *out_exp, double *out_log);
+
 #ifdef __cplusplus
 }
 #endif
