@@ -55,23 +55,41 @@ static int compile_bp(ldpc_code *c) {
         c->csc_edge[p] = e;
         csc_pos[e] = p;
     }
-    std::vector<BpEdgeC> ec(E);
-    std::vector<BpEdgeV> ev(E);
-    for (int r = 0; r < m; ++r) {
-        c->max_row_deg = std::max(c->max_row_deg, c->row_ptr[r + 1] - c->row_ptr[r]);
-        for (int e = c->row_ptr[r]; e < c->row_ptr[r + 1]; ++e)
-            ec[e] = BpEdgeC{(uint16_t) c->row_ptr[r], (uint16_t) c->row_ptr[r + 1], (uint16_t) csc_pos[e], 0};
+    for (int r = 0; r < m; ++r) c->max_row_deg = std::max(c->max_row_deg, c->row_ptr[r + 1] - c->row_ptr[r]);
+    // rank nodes by degree (stable), dropping degree-0 nodes, and record the degree classes
+    auto rank_by_degree = [](int count, const std::vector<int> &ptr, std::vector<int> &order,
+                             std::vector<BpClass> &classes) {
+        order.clear();
+        for (int i = 0; i < count; ++i)
+            if (ptr[i + 1] > ptr[i]) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return ptr[a + 1] - ptr[a] < ptr[b + 1] - ptr[b]; });
+        classes.clear();
+        for (int k = 0; k < (int) order.size(); ++k) {
+            const int d = ptr[order[k] + 1] - ptr[order[k]];
+            if (classes.empty() || classes.back().degree != d) classes.push_back(BpClass{d, k, 0});
+            classes.back().count++;
+        }
+    };
+    std::vector<int> chk_order, var_order;
+    rank_by_degree(m, c->row_ptr, chk_order, c->chk_classes);
+    rank_by_degree(n, c->col_ptr, var_order, c->var_classes);
+    std::vector<uint16_t> chk_rs(chk_order.size());
+    for (size_t k = 0; k < chk_order.size(); ++k) chk_rs[k] = (uint16_t) c->row_ptr[chk_order[k]];
+    std::vector<BpVarRec> var_rec(var_order.size());
+    std::vector<uint16_t> var_edges;
+    for (size_t k = 0; k < var_order.size(); ++k) {
+        const int v = var_order[k];
+        var_rec[k] = BpVarRec{(uint16_t) v, (uint16_t) var_edges.size()};
+        for (int p = c->col_ptr[v]; p < c->col_ptr[v + 1]; ++p) var_edges.push_back((uint16_t) c->csc_edge[p]);
     }
-    for (int v = 0; v < n; ++v)
-        for (int p = c->col_ptr[v]; p < c->col_ptr[v + 1]; ++p)
-            ev[p] = BpEdgeV{(uint16_t) c->col_ptr[v], (uint16_t) c->col_ptr[v + 1], (uint16_t) v,
-                            (uint16_t) c->csc_edge[p]};
     std::vector<uint16_t> colp(c->col_ptr.begin(), c->col_ptr.end());
     std::vector<uint16_t> rowp(c->row_ptr.begin(), c->row_ptr.end());
     std::vector<uint16_t> coli(c->col_idx.begin(), c->col_idx.end());
     int st;
-    if ((st = upload(&c->d.bp_c, ec))) return st;
-    if ((st = upload(&c->d.bp_v, ev))) return st;
+    if ((st = upload(&c->d.chk_rs, chk_rs))) return st;
+    if ((st = upload(&c->d.var_rec, var_rec))) return st;
+    if ((st = upload(&c->d.var_edges, var_edges))) return st;
     if ((st = upload(&c->d.col_ptr, colp))) return st;
     if ((st = upload(&c->d.row_ptr, rowp))) return st;
     if ((st = upload(&c->d.col_idx, coli))) return st;
@@ -237,7 +255,8 @@ int ldpc_code_create_dense(int32_t m, int32_t n, const uint8_t *H, int device, l
 void ldpc_code_destroy(ldpc_code_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d.bp_c); cudaFree(c->d.bp_v); cudaFree(c->d.col_ptr); cudaFree(c->d.row_ptr);
+    cudaFree(c->d.chk_rs); cudaFree(c->d.var_rec); cudaFree(c->d.var_edges); cudaFree(c->d.col_ptr);
+    for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); } cudaFree(c->d.row_ptr);
     cudaFree(c->d.col_idx); cudaFree(c->d.blocks); cudaFree(c->d.blk_order); cudaFree(c->d.var_ptr); cudaFree(c->d.inc);
     cudaFree(c->d.var_order); cudaFree(c->d.var_e); cudaFree(c->d.gen_cols);
     delete c;

@@ -5,6 +5,8 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -24,20 +26,25 @@ int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
     } while (0)
 
 // ---- device tables ----------------------------------------------------------
-// BP works per EDGE.  Edges have two numberings: the CSR position e (check-major,
-// V->C messages live in this order) and the CSC position p (variable-major, C->V
-// messages live in this order), so both phases gather from contiguous runs.
-struct BpEdgeC {      // indexed by CSR position e: what the check-side update of edge e needs
-    uint16_t begin;   // first CSR position of e's check
-    uint16_t end;     // one past the last
-    uint16_t dst;     // CSC position the C->V message is written to
+// BP works per NODE.  All messages of a frame live in ONE array indexed by the CSR
+// position of the edge: the variable phase reads the C->V message of an edge and
+// overwrites it with the V->C message, the check phase does the opposite, so each
+// phase updates its node's edges in place.  Nodes are ranked by degree so that a
+// warp runs one degree-specialised, fully unrolled code path.
+struct BpVarRec {
+    uint16_t var;     // variable index
+    uint16_t off;     // start of its edge list (CSR positions, rows ascending) in var_edges
+};
+struct BpJob {        // the work of one warp in one round: node ranks [first, first + count) x F frames
+    uint16_t degree;  // 0 = nothing to do
+    uint16_t first;
+    uint16_t count;
     uint16_t pad;
 };
-struct BpEdgeV {      // indexed by CSC position p: what the variable-side update needs
-    uint16_t begin;   // first CSC position of p's variable
-    uint16_t end;
-    uint16_t var;     // variable index (for the channel LLR)
-    uint16_t dst;     // CSR position the V->C message is written to
+struct BpClass { int degree, first, count; };
+struct BpSchedule {   // device arrays, rounds x warps jobs each
+    BpJob *jobs_v = nullptr, *jobs_c = nullptr;
+    int rounds_v = 0, rounds_c = 0;
 };
 
 // QP-ADMM works per BLOCK: one three-variable check of the chain decomposition
@@ -52,8 +59,9 @@ struct AdmmBlock {
 
 struct DeviceTables {
     // BP
-    BpEdgeC *bp_c = nullptr;
-    BpEdgeV *bp_v = nullptr;
+    uint16_t *chk_rs = nullptr;    // check rank -> CSR position of its first edge
+    BpVarRec *var_rec = nullptr;   // variable rank -> record
+    uint16_t *var_edges = nullptr; // E: CSR positions of the edges of each variable
     uint16_t *col_ptr = nullptr;   // n+1, CSC offsets
     uint16_t *row_ptr = nullptr;   // m+1
     uint16_t *col_idx = nullptr;   // E, variable of CSR position e
@@ -78,7 +86,11 @@ struct ldpc_code {
     int k = 0, k_words = 0;
     // host copies (also used by tests through ldpc_code_info)
     std::vector<int> row_ptr, col_idx, col_ptr, csc_edge;
+    std::vector<ldpc::BpClass> chk_classes, var_classes;   // nodes of equal degree are adjacent in rank order
     ldpc::DeviceTables d;
+    // BP launch schedules, built on first use per (frames per CTA, warps per CTA)
+    mutable std::mutex sched_mu;
+    mutable std::map<std::pair<int, int>, ldpc::BpSchedule> bp_sched;
 };
 
 namespace ldpc {

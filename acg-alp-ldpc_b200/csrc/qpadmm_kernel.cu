@@ -213,6 +213,8 @@ static void admm_shape(const ldpc_code *c, int *kb_out, int *threads_out) {
     int best_kb = 1, best_nt = 32;
     double best = -1;
     const char *force = getenv("LDPC_ADMM_KB");
+    if (force && (atoi(force) < 1 || atoi(force) > 8 || (c->n_blocks + atoi(force) - 1) / atoi(force) > 512))
+        force = nullptr;   // not a usable shape for this code: fall back to the heuristic
     for (int kb = 1; kb <= 8; ++kb) {
         if (force && atoi(force) != kb) continue;
         int nt = ((c->n_blocks + kb - 1) / kb + 31) / 32 * 32;

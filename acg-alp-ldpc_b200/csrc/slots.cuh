@@ -26,7 +26,7 @@ struct SlotBlock {
     int state[F];
     int hamming[F];     // channel hard-decision errors of the frame (experiment.h:33-46)
     int red[32];        // block-reduction scratch
-    unsigned bad;       // BP: byte f != 0 <=> some check of slot f is unsatisfied
+    unsigned bad;       // BP: bit f set <=> some check of slot f is unsatisfied
     int alive;          // slots that still hold or may get a frame
     unsigned info[F][16];
     unsigned long long cnt[LDPC_CNT_COUNT];
@@ -78,12 +78,12 @@ __device__ __forceinline__ int block_sum(int x, SlotBlock<F> *S) {
 }
 
 // LLRs (2 y / sigma^2, utils/channel.h:14-16) of the frames entering the slots of
-// `newmask`, interleaved as llr[i * F + f]; experiment mode also produces the
+// `newmask`, frame-major as llr[f * stride + i]; experiment mode also produces the
 // transmitted codeword cw[f * n + i] and the channel Hamming count.  `per_var(i, f,
 // llr)` lets the kernel initialise per-variable state.  Ends with a barrier.
 template <int F, typename PerVar>
 __device__ __forceinline__ void slots_load(const KernelIO &io, SlotBlock<F> *S, unsigned newmask, double *llr,
-                                           uint8_t *cw, PerVar per_var) {
+                                           int stride, uint8_t *cw, PerVar per_var) {
     const int n = io.n;
     if (!io.experiment) {
 #pragma unroll
@@ -92,7 +92,7 @@ __device__ __forceinline__ void slots_load(const KernelIO &io, SlotBlock<F> *S, 
             const double *y = io.y + (size_t) S->frame[f] * n;
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const double l = __ddiv_rn(__dmul_rn(2.0, y[i]), io.var);
-                llr[i * F + f] = l;
+                llr[(size_t) f * stride + i] = l;
                 per_var(i, f, l);
             }
         }
@@ -149,7 +149,7 @@ __device__ __forceinline__ void slots_load(const KernelIO &io, SlotBlock<F> *S, 
                     const double y = __fma_rn(io.sigma, z[h], bit ? -1.0 : 1.0);
                     ham += bit ? (y > 0) : (y <= 0);
                     const double l = __ddiv_rn(__dmul_rn(2.0, y), io.var);
-                    llr[i * F + f] = l;
+                    llr[(size_t) f * stride + i] = l;
                     per_var(i, f, l);
                 }
             }
