@@ -88,7 +88,7 @@ __device__ __forceinline__ void var_update(double *msg, const double *llr, doubl
     for (int j = 0; j < d; ++j) {
         const double others = (j == 0) ? suf[0] : (j == d - 1 ? pre : pre + suf[j]);
         const double t = l + others;                       // bp.h:81
-        const double e = exp_neg(fabs(t));
+        const double e = exp_neg_abs(t);
         const int sign_bit = t <= 0.0 ? (int) 0x80000000 : 0;   // bp.h:82: zero counts as negative
         msg[pos[j]] = with_hi(e, __double2hiint(e) | sign_bit | hard_bit);
         pre = (j == 0) ? m[0] : pre + m[j];
@@ -355,6 +355,23 @@ int launch_bp(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var
     while (F > 1 && bp_smem_bytes(c, F) > 227 * 1024) F >>= 1;
     if (bp_smem_bytes(c, F) > 227 * 1024)
         return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
+    // register budget: 256-thread CTAs at 2 / 3 / 4 CTAs per SM (128 / 85 / 64 registers per thread)
+    int minb = 2;
+    if (const char *force = getenv("LDPC_BP_MINB")) minb = atoi(force);
+    if (threads > 256) minb = 0;
+    switch (F * 8 + minb) {
+        case 8 * 8 + 2: return launch_bp_f<8, 256, 2>(p, c, threads, frames, stream);
+        case 8 * 8 + 3: return launch_bp_f<8, 256, 3>(p, c, threads, frames, stream);
+        case 8 * 8 + 4: return launch_bp_f<8, 256, 4>(p, c, threads, frames, stream);
+        case 4 * 8 + 2: return launch_bp_f<4, 256, 2>(p, c, threads, frames, stream);
+        case 4 * 8 + 3: return launch_bp_f<4, 256, 3>(p, c, threads, frames, stream);
+        case 4 * 8 + 4: return launch_bp_f<4, 256, 4>(p, c, threads, frames, stream);
+        case 2 * 8 + 2: return launch_bp_f<2, 256, 2>(p, c, threads, frames, stream);
+        case 2 * 8 + 3: return launch_bp_f<2, 256, 3>(p, c, threads, frames, stream);
+        case 1 * 8 + 2: return launch_bp_f<1, 256, 2>(p, c, threads, frames, stream);
+        case 1 * 8 + 3: return launch_bp_f<1, 256, 3>(p, c, threads, frames, stream);
+        default: break;
+    }
     switch (F) {
         case 8: return launch_bp_f<8, 512, 1>(p, c, threads, frames, stream);
         case 4: return launch_bp_f<4, 512, 1>(p, c, threads, frames, stream);
