@@ -1,8 +1,8 @@
 // Host-side graph compiler: H (CSR) -> device tables, once per H.
 //
 // Replaces the reference's per-FRAME structure builds:
-//   from_biadjacency_matrix + TannerGraph/VNode/CNode  (algo/bp.h:97-153)  -> BP edge tables
-//   ConstructADMMProblem                               (algo/qp_admm.h:13-102) -> ADMM block tables
+//   from_biadjacency_matrix + TannerGraph/VNode/CNode  (algo/bp.h:97-153)  -> BP node tables (here)
+//   ConstructADMMProblem                               (algo/qp_admm.h:13-102) -> ADMM block tables (admm_layout.cu)
 // Only q (the LLRs) depends on the frame; everything else depends on H alone.
 #include <algorithm>
 #include <cmath>
@@ -49,12 +49,7 @@ static int compile_bp(ldpc_code *c) {
     }
     c->csc_edge.assign(E, 0);
     std::vector<int> fill(c->col_ptr.begin(), c->col_ptr.end() - 1);
-    std::vector<int> csc_pos(E);
-    for (int e = 0; e < E; ++e) {
-        int p = fill[c->col_idx[e]]++;
-        c->csc_edge[p] = e;
-        csc_pos[e] = p;
-    }
+    for (int e = 0; e < E; ++e) c->csc_edge[fill[c->col_idx[e]]++] = e;
     for (int r = 0; r < m; ++r) c->max_row_deg = std::max(c->max_row_deg, c->row_ptr[r + 1] - c->row_ptr[r]);
     // rank nodes by degree (stable), dropping degree-0 nodes, and record the degree classes
     auto rank_by_degree = [](int count, const std::vector<int> &ptr, std::vector<int> &order,
@@ -93,95 +88,6 @@ static int compile_bp(ldpc_code *c) {
     if ((st = upload(&c->d.col_ptr, colp))) return st;
     if ((st = upload(&c->d.row_ptr, rowp))) return st;
     if ((st = upload(&c->d.col_idx, coli))) return st;
-    return LDPC_OK;
-}
-
-// The chain decomposition of qp_admm.h:59-92 expressed as blocks.
-static int compile_admm(ldpc_code *c) {
-    const int m = c->m, n = c->n;
-    struct RawBlock { int var[3]; int nvars; int rows; };
-    std::vector<RawBlock> raw;
-    int next_aux = n;
-    for (int r = 0; r < m; ++r) {
-        const int *idx = c->col_idx.data() + c->row_ptr[r];
-        int d = c->row_ptr[r + 1] - c->row_ptr[r];
-        if (d == 0) continue;                                    // qp_admm.h:67-69
-        if (d == 1) { raw.push_back({{idx[0], -1, -1}, 1, 1}); continue; }       // :70-74
-        if (d == 2) { raw.push_back({{idx[0], idx[1], -1}, 2, 2}); continue; }   // :75-83
-        int last = idx[0];                                       // :84-91
-        for (int j = 1; j <= d - 2; ++j) {
-            int third = (j == d - 2) ? idx[d - 1] : next_aux++;
-            raw.push_back({{last, idx[j], third}, 3, 4});
-            last = third;
-        }
-    }
-    c->n_blocks = (int) raw.size();
-    c->n_var = next_aux;
-    if (c->n_var >= 65535 || c->n_blocks >= 16384)
-        return fail(LDPC_E_UNSUPPORTED, "code too large for the 16-bit QP-ADMM tables");
-
-    std::vector<AdmmBlock> blocks(raw.size());
-    std::vector<std::vector<uint16_t>> inc(c->n_var);
-    std::vector<int> e(c->n_var, 0);
-    c->n_rows = 0;
-    c->nnz = 0;
-    for (size_t b = 0; b < raw.size(); ++b) {
-        const RawBlock &rb = raw[b];
-        int order[3] = {0, 1, 2};
-        // ascending variable index; absent slots (-1) go last and point at the zero sentinel
-        std::sort(order, order + 3, [&](int x, int y) {
-            int vx = rb.var[x] < 0 ? 1 << 30 : rb.var[x], vy = rb.var[y] < 0 ? 1 << 30 : rb.var[y];
-            return vx < vy || (vx == vy && x < y);
-        });
-        AdmmBlock ab;
-        ab.meta = (uint16_t) (rb.rows << 8);
-        for (int k = 0; k < 3; ++k) {
-            int slot = order[k];
-            ab.var[k] = (uint16_t) (rb.var[slot] < 0 ? c->n_var : rb.var[slot]);
-            ab.meta |= (uint16_t) (slot << (2 * k));
-        }
-        blocks[b] = ab;
-        for (int slot = 0; slot < rb.nvars; ++slot) {
-            inc[rb.var[slot]].push_back((uint16_t) ((b << 2) | slot));
-            e[rb.var[slot]] += rb.rows;          // one +-1 coefficient per row of the block
-        }
-        c->n_rows += rb.rows;
-        c->nnz += rb.rows * rb.nvars;
-    }
-    std::vector<uint32_t> var_ptr(c->n_var + 1, 0);
-    std::vector<uint16_t> inc_flat;
-    for (int v = 0; v < c->n_var; ++v) {
-        var_ptr[v] = (uint32_t) inc_flat.size();
-        inc_flat.insert(inc_flat.end(), inc[v].begin(), inc[v].end());
-    }
-    var_ptr[c->n_var] = (uint32_t) inc_flat.size();
-    c->n_inc = (int) inc_flat.size();
-    // e_min as DecodeQPADMM computes it: over ALL variables, starting from 1e9 (qp_admm.h:108-111)
-    c->e_min = 1000000000;
-    for (int v = 0; v < c->n_var; ++v) c->e_min = std::min(c->e_min, e[v]);
-    // balance: threads take variables round-robin from this order, so a warp sees equal degrees
-    std::vector<uint16_t> order(c->n_var);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](uint16_t a, uint16_t b) { return inc[a].size() > inc[b].size(); });
-    std::vector<uint8_t> e8(c->n_var);
-    for (int v = 0; v < c->n_var; ++v) {
-        if (e[v] > 255) return fail(LDPC_E_UNSUPPORTED, "column weight too large for the QP-ADMM tables");
-        e8[v] = (uint8_t) e[v];
-    }
-    // blocks grouped by the order in which their slots are visited (at most three patterns occur)
-    std::vector<uint16_t> blk_order(raw.size());
-    std::iota(blk_order.begin(), blk_order.end(), 0);
-    std::stable_sort(blk_order.begin(), blk_order.end(), [&](uint16_t a, uint16_t b) {
-        return (blocks[a].meta & 0x3f) < (blocks[b].meta & 0x3f);
-    });
-    int st;
-    if ((st = upload(&c->d.blocks, blocks))) return st;
-    if ((st = upload(&c->d.blk_order, blk_order))) return st;
-    if ((st = upload(&c->d.var_ptr, var_ptr))) return st;
-    if ((st = upload(&c->d.inc, inc_flat))) return st;
-    if ((st = upload(&c->d.var_order, order))) return st;
-    if ((st = upload(&c->d.var_e, e8))) return st;
     return LDPC_OK;
 }
 
@@ -255,10 +161,11 @@ int ldpc_code_create_dense(int32_t m, int32_t n, const uint8_t *H, int device, l
 void ldpc_code_destroy(ldpc_code_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d.chk_rs); cudaFree(c->d.var_rec); cudaFree(c->d.var_edges); cudaFree(c->d.col_ptr);
-    for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); } cudaFree(c->d.row_ptr);
-    cudaFree(c->d.col_idx); cudaFree(c->d.blocks); cudaFree(c->d.blk_order); cudaFree(c->d.var_ptr); cudaFree(c->d.inc);
-    cudaFree(c->d.var_order); cudaFree(c->d.var_e); cudaFree(c->d.gen_cols);
+    cudaFree(c->d.chk_rs); cudaFree(c->d.var_rec); cudaFree(c->d.var_edges);
+    cudaFree(c->d.col_ptr); cudaFree(c->d.row_ptr); cudaFree(c->d.col_idx);
+    cudaFree(c->d.blocks); cudaFree(c->d.admm_var); cudaFree(c->d.admm_inc); cudaFree(c->d.admm_var_id); cudaFree(c->d.admm_var_rank);
+    cudaFree(c->d.gen_cols);
+    for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
     delete c;
 }
 
@@ -268,11 +175,14 @@ int ldpc_code_info(const ldpc_code_t *c, ldpc_code_info_t *info) {
     info->max_row_deg = c->max_row_deg; info->max_col_deg = c->max_col_deg;
     info->admm_blocks = c->n_blocks; info->admm_n_var = c->n_var; info->admm_rows = c->n_rows;
     info->admm_nnz = c->nnz; info->admm_e_min = c->e_min; info->k = c->k; info->device = c->device;
+    info->admm_conflicts_natural = (int32_t) c->admm_conflicts_before;
+    info->admm_conflicts_laid_out = (int32_t) c->admm_conflicts_after;
     return LDPC_OK;
 }
 
 int ldpc_code_set_generator(ldpc_code_t *c, int32_t k, const uint8_t *G) {
     if (!c || !G || k <= 0) return fail(LDPC_E_INVALID, "bad generator");
+    if (k > 512) return fail(LDPC_E_UNSUPPORTED, "generators with more than 512 rows are not supported");
     LDPC_CUDA(cudaSetDevice(c->device));
     int kw = (k + 31) / 32;
     std::vector<uint32_t> cols((size_t) c->n * kw, 0u);

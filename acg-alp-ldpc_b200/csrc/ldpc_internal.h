@@ -51,10 +51,19 @@ struct BpSchedule {   // device arrays, rounds x warps jobs each
 // (qp_admm.h:34-57, 84-91) with its 4 inequality rows, or a degree-2 / degree-1
 // check (2 rows / 1 row, qp_admm.h:70-83).  Row q of a block has coefficient +1
 // for slot q and for every slot in row 3, else -1.
-struct AdmmBlock {
-    uint16_t var[3];  // the block's variables in ASCENDING index order (the residual is
-                      // accumulated in that order, qp_admm.h:144-151); absent -> n_var (a zero)
+// Variables and blocks are addressed by RANK (their position in the kernel's processing
+// and storage order, chosen by admm_layout.cu to avoid shared-memory bank conflicts).
+struct AdmmBlock {    // indexed by block rank
+    uint16_t var[3];  // RANKS of the block's variables in ASCENDING variable-index order (the residual
+                      // is accumulated in that order, qp_admm.h:144-151); absent -> n_var (a zero)
     uint16_t meta;    // bits 0-1 / 2-3 / 4-5: slot of var[0] / var[1] / var[2]; bits 8-10: rows
+};
+struct AdmmVarRec {   // indexed by variable rank
+    uint16_t inc_start;   // first incidence word of the variable in admm_inc
+    uint8_t inc_count;    // number of blocks the variable belongs to
+    uint8_t pad0;
+    uint16_t e;           // sum of squared coefficients of its column (qp_admm.h:94-99)
+    uint16_t pad1;
 };
 
 struct DeviceTables {
@@ -66,12 +75,12 @@ struct DeviceTables {
     uint16_t *row_ptr = nullptr;   // m+1
     uint16_t *col_idx = nullptr;   // E, variable of CSR position e
     // QP-ADMM
-    AdmmBlock *blocks = nullptr;   // n_blocks
-    uint16_t *blk_order = nullptr; // n_blocks: blocks grouped by slot pattern, so a warp runs one pattern
-    uint32_t *var_ptr = nullptr;   // n_var+1 offsets into inc
-    uint16_t *inc = nullptr;       // incidences (block << 2 | slot), block ascending per variable
-    uint16_t *var_order = nullptr; // n_var: variables sorted by degree (descending) for balance
-    uint8_t *var_e = nullptr;      // n_var: e_i = sum of squared coefficients of column i
+    AdmmBlock *blocks = nullptr;       // n_blocks, rank order
+    AdmmVarRec *admm_var = nullptr;    // n_var, rank order
+    uint32_t *admm_inc = nullptr;      // incidence words: block rank | sign-flip bits 31/30/29 for rows 0/1/2,
+                                       // blocks in ascending row order per variable (the reference's gather order)
+    uint16_t *admm_var_id = nullptr;   // variable rank -> variable index
+    uint16_t *admm_var_rank = nullptr; // variable index (< n) -> rank
     // generator (optional): column j of G packed over k bits, k_words words per column
     uint32_t *gen_cols = nullptr;
 };
@@ -84,6 +93,7 @@ struct ldpc_code {
     int max_row_deg = 0, max_col_deg = 0;
     int n_blocks = 0, n_var = 0, n_rows = 0, nnz = 0, n_inc = 0, e_min = 0;
     int k = 0, k_words = 0;
+    long admm_conflicts_before = 0, admm_conflicts_after = 0;   // replayed wavefronts per iteration (layout cost)
     // host copies (also used by tests through ldpc_code_info)
     std::vector<int> row_ptr, col_idx, col_ptr, csc_edge;
     std::vector<ldpc::BpClass> chk_classes, var_classes;   // nodes of equal degree are adjacent in rank order
@@ -111,6 +121,8 @@ struct FrameIO {
     uint64_t n_words = 0;
     unsigned long long *counters = nullptr;  // LDPC_CNT_COUNT device words
 };
+
+int compile_admm(ldpc_code *code);
 
 int launch_bp(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
               int early_exit, unsigned long long *queue, cudaStream_t stream);

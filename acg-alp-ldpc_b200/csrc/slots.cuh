@@ -1,10 +1,9 @@
 // Frame slots: the scheduling skeleton shared by the decoding kernels.
 //
 // A persistent CTA keeps F frames ("slots") in flight and advances them in lock
-// step, one decoder iteration per trip of its main loop.  A thread works on the
-// same graph element (edge / variable / block) of all F frames at once, which
-// amortises every index load, address computation and loop instruction over F
-// frames and gives F independent dependency chains per thread.  Frames finish at
+// step, one decoder iteration per trip of its main loop; a lane works on one
+// (graph element, frame) pair, so F frames fill the warps of a CTA even when the
+// graph has few nodes of one kind.  Frames finish at
 // very different iteration counts, so a slot whose frame has
 // finished is refilled from the global atomic frame queue at the top of the next
 // trip while its neighbours keep iterating: no slot waits for the slowest frame.
@@ -92,7 +91,7 @@ __device__ __forceinline__ void slots_load(const KernelIO &io, SlotBlock<F> *S, 
             const double *y = io.y + (size_t) S->frame[f] * n;
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const double l = __ddiv_rn(__dmul_rn(2.0, y[i]), io.var);
-                llr[(size_t) f * stride + i] = l;
+                if (llr) llr[(size_t) f * stride + i] = l;
                 per_var(i, f, l);
             }
         }
@@ -149,7 +148,7 @@ __device__ __forceinline__ void slots_load(const KernelIO &io, SlotBlock<F> *S, 
                     const double y = __fma_rn(io.sigma, z[h], bit ? -1.0 : 1.0);
                     ham += bit ? (y > 0) : (y <= 0);
                     const double l = __ddiv_rn(__dmul_rn(2.0, y), io.var);
-                    llr[(size_t) f * stride + i] = l;
+                    if (llr) llr[(size_t) f * stride + i] = l;
                     per_var(i, f, l);
                 }
             }

@@ -30,7 +30,8 @@ class LdpcError(RuntimeError):
 
 class CodeInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("m", "n", "edges", "max_row_deg", "max_col_deg", "admm_blocks",
-                                          "admm_n_var", "admm_rows", "admm_nnz", "admm_e_min", "k", "device")]
+                                          "admm_n_var", "admm_rows", "admm_nnz", "admm_e_min", "k", "device",
+                                          "admm_conflicts_natural", "admm_conflicts_laid_out")]
 
 
 class AlgoCfg(C.Structure):

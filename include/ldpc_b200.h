@@ -56,6 +56,9 @@ typedef struct {
     int32_t admm_e_min;  /* min_i sum_j A_ji^2, used by the feasibility test qp_admm.h:108-114 */
     int32_t k;           /* generator rows attached with ldpc_code_set_generator, else 0 */
     int32_t device;
+    /* shared-memory wavefronts replayed per QP-ADMM iteration because of bank conflicts, for the natural
+       ordering of variables/blocks and for the ordering the graph compiler chose */
+    int32_t admm_conflicts_natural, admm_conflicts_laid_out;
 } ldpc_code_info_t;
 
 /* Counter block of one Monte-Carlo point.  The first fields are the reference's

@@ -295,3 +295,33 @@ def test_full_size_properties(gpu_lib, codes):
     sigma = sqrt(10 ** 0.3 / 2)
     expect = n * 0.5 * erfc(1 / sigma / sqrt(2))
     assert abs(r["sum_hamming"] / r["total"] - expect) < 0.2
+
+
+@pytest.mark.parametrize("shape", [("1", "2"), ("1", "8"), ("2", "4"), ("2", "5"), ("4", "8")])
+def test_qpadmm_launch_shapes(codes, oracle, shape, monkeypatch):
+    """frames per CTA x blocks per lane: every shape is bit-identical to the oracle, whatever the schedule"""
+    monkeypatch.setenv("LDPC_ADMM_F", shape[0])
+    monkeypatch.setenv("LDPC_ADMM_KB", shape[1])
+    for name, frames, snr, iters in (("optimalH", 75, -3.0, 600), ("H05", 33, -2.0, 400), ("reg_3_6_1008", 9, -1.0, 200)):
+        H, code, csr = codes[name]
+        m, n = H.shape
+        alpha, mu = ADMM[name]
+        y = code.channel(SEED, 7000, frames, snr)
+        gb, gok, git, gv = code.qpadmm_decode(y, snr, alpha, mu, iters, 1e-5)
+        ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, iters, 1e-5)
+        assert (git == oit).all() and (gb == ob).all() and (gok == ook).all() and (gv == ov).all(), (name, shape)
+    H, code, csr = codes["optimalH"]
+    import ldpc_b200
+    dec = ldpc_b200.QPADMMDecoder(1.2, 0.55, 500, 1e-5)
+    got = code.experiment(dec, -2.5, SEED, 0, 70)
+    want = oracle.experiment("qpadmm", csr, H.shape[0], H.shape[1], -2.5, 500, SEED, 0, 70, alpha=1.2, mu=0.55, eps_stop=1e-5)
+    assert all(got[k] == want[k] for k in want)
+
+
+def test_admm_layout_removes_bank_conflicts(codes):
+    """the graph compiler's rank assignment (csrc/admm_layout.cu) must beat the natural order by a wide margin"""
+    for name in ("optimalH", "H05", "reg_3_6_1008"):
+        info = codes[name][1].info
+        print(name, "replayed wavefronts per iteration: natural", info["admm_conflicts_natural"], "laid out",
+              info["admm_conflicts_laid_out"])
+        assert info["admm_conflicts_laid_out"] * 4 <= info["admm_conflicts_natural"]
