@@ -37,28 +37,35 @@ struct Layout {
     std::vector<int> rank_v, rank_b;            // id -> rank
     std::vector<int> at_v, at_b;                // rank -> id
 
-    // replayed wavefronts of the w gather of variable ranks [8g, 8g+8)
-    int cost_vgroup(int g) const {
+    // The search minimises the number of clashing PAIRS (a smooth surrogate); the figure of merit
+    // reported to the caller is the number of replayed wavefronts (max multiplicity - 1 per access).
+    // w gather of variable ranks [8g, 8g+8): one access per step of the incidence lists
+    int cost_vgroup(int g, bool pairs = true) const {
         int cost = 0;
         for (int step = 0;; ++step) {
-            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, any = 0, worst = 0;
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen[8], any = 0, worst = 1, clash = 0;
+            for (int i = 0; i < 8; ++i) seen[i] = -1;
             for (int r = 8 * g; r < std::min(8 * g + 8, nv); ++r) {
                 const std::vector<int> &bl = var_blocks[at_v[r]];
                 if (step < (int) bl.size()) {
                     any = 1;
-                    worst = std::max(worst, ++cnt[rank_b[bl[step]] & 7]);
+                    const int bank = rank_b[bl[step]] & 7;
+                    if (seen[bank] == bl[step]) continue;     // same chunk: broadcast, not a conflict
+                    seen[bank] = bl[step];
+                    clash += cnt[bank];
+                    worst = std::max(worst, ++cnt[bank]);
                 }
             }
             if (!any) break;
-            cost += worst - 1;
+            cost += pairs ? clash : worst - 1;
         }
         return cost;
     }
-    // replayed wavefronts of the v gather of block ranks [16h, 16h+16)
-    int cost_bgroup(int h) const {
+    // v gather of block ranks [16h, 16h+16): one access per visited variable
+    int cost_bgroup(int h, bool pairs = true) const {
         int cost = 0;
         for (int k = 0; k < 3; ++k) {
-            int cnt[16] = {0}, worst = 1;
+            int cnt[16] = {0}, worst = 1, clash = 0;
             int seen[16];
             for (int i = 0; i < 16; ++i) seen[i] = -1;
             for (int r = 16 * h; r < std::min(16 * h + 16, nb); ++r) {
@@ -67,16 +74,17 @@ struct Layout {
                 const int bank = rank_v[v] & 15;
                 if (seen[bank] == v) continue;    // same address: broadcast, not a conflict
                 seen[bank] = v;
+                clash += cnt[bank];
                 worst = std::max(worst, ++cnt[bank]);
             }
-            cost += worst - 1;
+            cost += pairs ? clash : worst - 1;
         }
         return cost;
     }
-    long total_cost() const {
+    long replayed_wavefronts() const {
         long c = 0;
-        for (int g = 0; 8 * g < nv; ++g) c += cost_vgroup(g);
-        for (int h = 0; 16 * h < nb; ++h) c += cost_bgroup(h);
+        for (int g = 0; 8 * g < nv; ++g) c += cost_vgroup(g, false);
+        for (int h = 0; 16 * h < nb; ++h) c += cost_bgroup(h, false);
         return c;
     }
 };
@@ -218,11 +226,15 @@ int compile_admm(ldpc_code *c) {
     L.rank_v.resize(nv); L.rank_b.resize(nb);
     for (int r = 0; r < nv; ++r) L.rank_v[L.at_v[r]] = r;
     for (int r = 0; r < nb; ++r) L.rank_b[L.at_b[r]] = r;
-    c->admm_conflicts_before = L.total_cost();
-    int moves = 120 * (nv + nb);
+    c->admm_conflicts_before = L.replayed_wavefronts();
+    int moves = 40 * (nv + nb);   // ~40 ms for the 160 x 280 codes; H changes per proposal in optimize_H.cpp
     if (const char *s = getenv("LDPC_ADMM_LAYOUT_MOVES")) moves = atoi(s);
-    if (moves > 0) anneal(L, moves);
-    c->admm_conflicts_after = L.total_cost();
+    if (moves > 0) {
+        Layout start = L;
+        anneal(L, moves);
+        if (L.replayed_wavefronts() > start.replayed_wavefronts()) L = start;   // never worse than the natural order
+    }
+    c->admm_conflicts_after = L.replayed_wavefronts();
 
     // ---- device tables in rank order
     std::vector<AdmmVarRec> vrec(nv);

@@ -289,6 +289,11 @@ int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *
     return debug_bpmath(device, count, a, ev, od, out_exp, out_log);
 }
 
+int ldpc_measure_smem_peak(int device, double *gbytes_per_s) {
+    if (!gbytes_per_s) return fail(LDPC_E_INVALID, "NULL argument");
+    return measure_smem_peak(device, gbytes_per_s);
+}
+
 int ldpc_measure_fp64_peak(int device, double *gfma_per_s) {
     if (!gfma_per_s) return fail(LDPC_E_INVALID, "NULL argument");
     return measure_fp64_peak(device, gfma_per_s);

@@ -134,3 +134,50 @@ int measure_fp64_peak(int device, double *gfma_per_s) {
 }
 
 }  // namespace ldpc
+
+namespace ldpc {
+
+// conflict-free 16-byte shared-memory loads, 4 independent per iteration: measures bytes/clk x clock of the LSU path
+__global__ void smem_peak_kernel(double *out, int iters) {
+    __shared__ __align__(16) double2 buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_double2(i, -i);
+    __syncthreads();
+    double2 a0 = make_double2(0, 0), a1 = a0, a2 = a0, a3 = a0;
+    int idx = threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+        const double2 x0 = buf[idx], x1 = buf[(idx + 256) & 2047], x2 = buf[(idx + 512) & 2047], x3 = buf[(idx + 768) & 2047];
+        a0.x += x0.x; a1.y += x1.y; a2.x += x2.x; a3.y += x3.y;
+        idx = (idx + 1024 + (int) (x0.y == 12345.0)) & 2047;      // data dependence keeps the loads in the loop
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (a0.x + a1.y) + (a2.x + a3.y);
+}
+
+int measure_smem_peak(int device, double *gbytes_per_s) {
+    LDPC_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int threads = 256, blocks = sms * 4, iters = 1 << 14;
+    double *out = nullptr;
+    LDPC_CUDA(cudaMalloc((void **) &out, sizeof(double) * threads * blocks));
+    cudaEvent_t e0, e1;
+    LDPC_CUDA(cudaEventCreate(&e0));
+    LDPC_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        LDPC_CUDA(cudaEventRecord(e0));
+        smem_peak_kernel<<<blocks, threads>>>(out, iters);
+        LDPC_CUDA(cudaEventRecord(e1));
+        LDPC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        LDPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double) threads * blocks * 4.0 * 16.0 * iters / (ms * 1e-3) / 1e9;
+        if (rep >= 2 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *gbytes_per_s = best;
+    return LDPC_OK;
+}
+
+}  // namespace ldpc

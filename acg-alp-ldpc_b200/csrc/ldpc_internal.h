@@ -133,6 +133,7 @@ int launch_channel(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, i
 int launch_generator_codewords(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames,
                                uint8_t *d_codewords, cudaStream_t stream);
 int measure_fp64_peak(int device, double *gfma_per_s);
+int measure_smem_peak(int device, double *gbytes_per_s);
 int debug_bpmath(int device, int count, const double *a, const double *ev, const double *od, double *out_exp,
                  double *out_log);
 

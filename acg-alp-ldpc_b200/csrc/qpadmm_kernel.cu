@@ -2,10 +2,9 @@
 //
 // A persistent CTA keeps F frames in flight (slots.cuh); a lane is an (element,
 // frame) pair and the whole iteration state stays on chip:
-//   registers      t[row] = r - yl of the previous iteration, 4 rows per block, KB
-//                  blocks per thread.  z = max(t, 0) and yl = max(-t, 0)
-//                  (qp_admm.h:156-157: yl - r == -(r - yl) exactly), so one double per
-//                  inequality row replaces the reference's z[] and yl[].
+//   registers      yl[row], the dual of the previous iteration, 4 rows per block, KB blocks
+//                  per lane.  The reference's z[] is not state: it is only read through
+//                  w below, and yl' = max(0, yl - r) = max(0, -(r - yl)) exactly.
 //   shared memory  per frame: w = yl + mu (z - b) of block rank R as two 16-byte chunks
 //                  w01[R], w23[R] (the only form in which z, yl are read by the v-update,
 //                  qp_admm.h:137); v and q + alpha/2 of variable rank R.  Per CTA:
@@ -57,15 +56,29 @@ __device__ __forceinline__ double flip_by(double x, uint32_t word) {
 // q == 3 or q == s, else -1.  The leading "0 -/+ v" of rows 0..2 is folded into a
 // sign (differs from the reference only in the sign of an exact zero).
 template <int S0, int S1, int S2>
-__device__ __forceinline__ void residual_rows(const double vs[3], double b3, double r[4]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const bool p0 = (q == 3 || q == S0), p1 = (q == 3 || q == S1), p2 = (q == 3 || q == S2);
-        double x = (q == 3) ? __dadd_rn(b3, -vs[0]) : (p0 ? -vs[0] : vs[0]);
-        x = __dadd_rn(x, p1 ? -vs[1] : vs[1]);
-        x = __dadd_rn(x, p2 ? -vs[2] : vs[2]);
-        r[q] = x;
-    }
+__device__ __forceinline__ void residual_rows(double v0, double v1, double v2, double b3, double &r0, double &r1,
+                                              double &r2, double &r3) {
+    // row q: x = (q == 3 ? b3 - v0 : -+v0), then -+ v1, then -+ v2, minus where cf = +1
+    r0 = __dadd_rn(__dadd_rn(S0 == 0 ? -v0 : v0, S1 == 0 ? -v1 : v1), S2 == 0 ? -v2 : v2);
+    r1 = __dadd_rn(__dadd_rn(S0 == 1 ? -v0 : v0, S1 == 1 ? -v1 : v1), S2 == 1 ? -v2 : v2);
+    r2 = __dadd_rn(__dadd_rn(S0 == 2 ? -v0 : v0, S1 == 2 ? -v1 : v1), S2 == 2 ? -v2 : v2);
+    r3 = __dadd_rn(__dadd_rn(__dadd_rn(b3, -v0), -v1), -v2);
+}
+
+// One inequality row (qp_admm.h:154-159): yl is the dual of the previous iteration (state), r the new
+// residual.  t = r - yl; z = max(0, t); yl' = max(0, -t) (== max(0, yl - r) exactly); stop-sum term (z - r)^2;
+// w = yl' + mu (z - b).  Returns w, updates yl and part.
+template <bool ROW3>
+__device__ __forceinline__ double row_update(double r, double &yl, double &part, double mu, double b3) {
+    const double t = __dadd_rn(r, -yl);
+    // both maxima from the sign bit alone, on the integer pipe (bit-identical to std::max, signed zeros included)
+    const int hi = __double2hiint(t), lo = __double2loint(t);
+    const int neg = hi >> 31;                                          // all ones iff t < 0 (or t == -0)
+    const double z = __hiloint2double(hi & ~neg, lo & ~neg);           // max(0, t)
+    yl = __hiloint2double(hi & neg & 0x7fffffff, lo & neg);            // max(0, -t)
+    const double d = __dadd_rn(z, -r);
+    part = __fma_rn(d, d, part);
+    return __fma_rn(mu, ROW3 ? __dadd_rn(z, -b3) : z, yl);
 }
 
 template <int F, int KB>
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(512) qpadmm_kernel(const AdmmParams p) {
                         qa[(size_t) f_lane * p.stride_v + r] = half_alpha;
                         v_f[r] = 0.0;
                     }
-                // z = yl = 0  ->  t = 0, w = mu * (0 - b)
+                // z = yl = 0 (t[][] holds yl), w = mu * (0 - b)
 #pragma unroll
                 for (int k = 0; k < KB; ++k) {
                     t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0.0;
@@ -192,33 +205,29 @@ __global__ void __launch_bounds__(512) qpadmm_kernel(const AdmmParams p) {
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 if (!have[k]) continue;
-                const int rows = blk[k].meta >> 8;
-                const double vs[3] = {v_f[blk[k].var[0]], v_f[blk[k].var[1]], v_f[blk[k].var[2]]};
-                const double b3 = rows == 4 ? 2.0 : 0.0;
-                double r[4];
-                switch (blk[k].meta & 0x3f) {
-                    case 0x24: residual_rows<0, 1, 2>(vs, b3, r); break;   // slots visited 0,1,2
-                    case 0x21: residual_rows<1, 0, 2>(vs, b3, r); break;   // 1,0,2
-                    default:   residual_rows<1, 2, 0>(vs, b3, r); break;   // 1,2,0 (0x09)
+                const int meta = blk[k].meta;
+                const double v0 = v_f[blk[k].var[0]], v1 = v_f[blk[k].var[1]], v2 = v_f[blk[k].var[2]];
+                double r0, r1, r2, r3, w0, w1, w2, w3;
+                if ((meta >> 8) == 4) {              // a three-variable check: the common, branch-free case
+                    switch (meta & 0x3f) {
+                        case 0x24: residual_rows<0, 1, 2>(v0, v1, v2, 2.0, r0, r1, r2, r3); break;   // slots visited 0,1,2
+                        case 0x21: residual_rows<1, 0, 2>(v0, v1, v2, 2.0, r0, r1, r2, r3); break;   // 1,0,2
+                        default:   residual_rows<1, 2, 0>(v0, v1, v2, 2.0, r0, r1, r2, r3); break;   // 1,2,0 (0x09)
+                    }
+                    w0 = row_update<false>(r0, t[k][0], part, p.mu, 2.0);
+                    w1 = row_update<false>(r1, t[k][1], part, p.mu, 2.0);
+                    w2 = row_update<false>(r2, t[k][2], part, p.mu, 2.0);
+                    w3 = row_update<true>(r3, t[k][3], part, p.mu, 2.0);
+                } else {                             // degree-1 / degree-2 checks (slots 0,1,2 in order, b = 0):
+                    const int rows = meta >> 8;      // the missing rows stay identically zero
+                    residual_rows<0, 1, 2>(v0, v1, v2, 0.0, r0, r1, r2, r3);
+                    w0 = row_update<false>(r0, t[k][0], part, p.mu, 0.0);
+                    w1 = row_update<false>(rows < 2 ? 0.0 : r1, t[k][1], part, p.mu, 0.0);
+                    w2 = row_update<false>(0.0, t[k][2], part, p.mu, 0.0);
+                    w3 = row_update<false>(0.0, t[k][3], part, p.mu, 0.0);
                 }
-                double wn[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double rq = q < rows ? r[q] : 0.0;
-                    const double told = t[k][q];
-                    const double yl_old = (told < 0.0) ? -told : 0.0;
-                    const double tn = __dadd_rn(rq, -yl_old);
-                    const bool pos = 0.0 < tn;
-                    const double z = pos ? tn : 0.0;
-                    const double yl = pos ? 0.0 : -tn;
-                    const double d = __dadd_rn(z, -rq);
-                    part = __fma_rn(d, d, part);
-                    const double zb = (q == 3) ? __dadd_rn(z, -b3) : z;
-                    wn[q] = __fma_rn(p.mu, zb, yl);
-                    t[k][q] = tn;
-                }
-                w01_f[k * ne + elem] = make_double2(wn[0], wn[1]);
-                w23_f[k * ne + elem] = make_double2(wn[2], wn[3]);
+                w01_f[k * ne + elem] = make_double2(w0, w1);
+                w23_f[k * ne + elem] = make_double2(w2, w3);
             }
         }
         // the lanes of one frame are LPF consecutive lanes of the warp
@@ -334,8 +343,11 @@ static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int 
             LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s.threads, s.smem));
             if (per_sm < 1) continue;
             const double lanes_busy = (double) c->n_blocks * F / ((double) kb * s.threads);
-            const double warps = std::min(per_sm * s.threads / 32.0, 24.0);
-            const double score = warps * lanes_busy;
+            // measured on B200 (profiles/r01_admm_sweep.txt): throughput follows the number of frames resident
+            // per SM (the dual state lives in registers, so 3..5 frames fit) times the lane utilisation;
+            // more than 6 blocks per lane serialises too much work behind one dependency chain
+            const double frames_per_sm = std::min(per_sm * F, 6);
+            const double score = frames_per_sm * lanes_busy * (kb <= 6 ? 1.0 : 0.75);
             if (score > best_score + 1e-9) { best_score = score; *out = s; *per_sm_out = per_sm; }
         }
     }

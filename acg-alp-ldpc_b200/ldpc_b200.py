@@ -72,6 +72,7 @@ def lib():
     L.ldpc_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.ldpc_host_free.argtypes = [vp]
     L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
+    L.ldpc_measure_smem_peak.argtypes = [C.c_int, C.POINTER(dbl)]
     L.ldpc_debug_bpmath.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -91,6 +92,12 @@ def device_count():
 def measure_fp64_peak(device=0):
     out = C.c_double()
     _check(lib().ldpc_measure_fp64_peak(device, C.byref(out)))
+    return out.value
+
+
+def measure_smem_peak(device=0):
+    out = C.c_double()
+    _check(lib().ldpc_measure_smem_peak(device, C.byref(out)))
     return out.value
 
 

@@ -1,0 +1,135 @@
+// Local-descent search over quasi-cyclic parity-check matrices (circulant blocks of
+// size 20 on an 8 x 14 grid) that minimises the QP-ADMM frame error rate -- the
+// reference's optimize_H.cpp (:12-137) with the FER evaluation on the GPU.
+// The proposal chain is the reference's: mt19937(239) drives random_permute, a
+// proposal is accepted iff its FER is strictly lower, every accepted matrix is
+// written to the save path.  Every proposal is a new H, hence a new code handle.
+//
+// Environment: LDPC_OPT_ITERS (default 10000), LDPC_OPT_SAVE (default data/optimalH.txt),
+//              LDPC_OPT_START (a matrix stem to start from instead of a random one).
+#include <memory>
+#include <utility>
+
+#include "experiment.h"
+#include "utils/parse_data.h"
+#include "utils/codeword.h"
+#include "algo/algo.h"
+#include "algo/qp_admm.h"
+
+using namespace std;
+
+const int THREADS_NUM = 200;
+double SNR = -3.0;
+shared_ptr<QPADMMDecoder> decoder = make_shared<QPADMMDecoder>(1.95, 0.5, 1000, 1e-5);
+
+// FER of the decoder on `tests_num` codewords of H drawn from mt19937(239); 1.0 when H is rank deficient
+double FER(const TMatrix &H, int tests_num = 1000) {
+    pair<TMatrix, bool> gen = GetOrtogonal(H);
+    if (!gen.second) return 1.0;
+    mt19937 rnd(239);
+    vector<TCodeword> codewords = gen_random_codewords(gen.first, tests_num, rnd);
+    return multithread_experiment(decoder, codewords, H, SNR, THREADS_NUM).FER();
+}
+
+// A block matrix whose (i, j) block is either zero or the identity cyclically shifted by diagonals[i][j].
+struct PermutationsMatrix {
+    PermutationsMatrix(int block_size, const TMatrix &blocks, const vector<vector<int>> &diagonals)
+        : _block_size(block_size), _blocks(blocks), _diagonals(diagonals) {}
+
+    // recover the block structure of a quasi-cyclic H (asserts that H is one)
+    PermutationsMatrix(int block_size, const TMatrix &H) : _block_size(block_size) {
+        assert(H.size() % block_size == 0 && H[0].size() % block_size == 0);
+        const int rows = (int) H.size() / block_size, cols = (int) H[0].size() / block_size;
+        _blocks.assign(rows, TCodeword(cols, false));
+        _diagonals.assign(rows, vector<int>(cols, -block_size));
+        for (int r = 0; r < (int) H.size(); ++r)
+            for (int c = 0; c < (int) H[0].size(); ++c) {
+                if (!H[r][c]) continue;
+                const int bi = r / block_size, bj = c / block_size;
+                const int shift = ((c % block_size) - (r % block_size) + block_size) % block_size;
+                assert(!_blocks[bi][bj] || _diagonals[bi][bj] == shift);
+                _blocks[bi][bj] = true;
+                _diagonals[bi][bj] = shift;
+            }
+        assert(to_tmatrix() == H);
+    }
+
+    TMatrix to_tmatrix() const {
+        const int rows = (int) _blocks.size(), cols = (int) _blocks[0].size();
+        TMatrix H(_block_size * rows, TCodeword(_block_size * cols, false));
+        for (int bi = 0; bi < rows; ++bi)
+            for (int bj = 0; bj < cols; ++bj) {
+                if (!_blocks[bi][bj]) continue;
+                const int shift = _diagonals[bi][bj];
+                assert(0 <= shift && shift < _block_size);
+                for (int k = 0; k < _block_size; ++k) H[bi * _block_size + k][bj * _block_size + (shift + k) % _block_size] = true;
+            }
+        return H;
+    }
+
+    // one move of the search: pick a block; switch it on if it is off, otherwise toss a coin on switching it
+    // off; then redraw its shift.  The generator is consumed in exactly this order (optimize_H.cpp:71-80).
+    template <typename Gen>
+    PermutationsMatrix random_permute(Gen &rnd) const {
+        const int i = rnd() % (int) _blocks.size();
+        const int j = rnd() % (int) _blocks[0].size();
+        PermutationsMatrix next(*this);
+        if (!next._blocks[i][j] or rnd() % 2 == 0) next._blocks[i][j] = !next._blocks[i][j];
+        next._diagonals[i][j] = rnd() % _block_size;
+        return next;
+    }
+
+private:
+    int _block_size;
+    TMatrix _blocks;
+    vector<vector<int>> _diagonals;
+};
+
+template <typename Gen>
+PermutationsMatrix optimize(PermutationsMatrix H, Gen &rnd, int iters, const string &save_filepath) {
+    double error = FER(H.to_tmatrix());
+    cout << "initial FER=" << error << endl;
+    for (int i = 0; i < iters; i++) {
+        PermutationsMatrix candidate = H.random_permute(rnd);
+        const double candidate_error = FER(candidate.to_tmatrix());
+        cout << "\tproposal: FER=" << candidate_error << endl;
+        if (candidate_error < error) {
+            H = candidate;
+            error = candidate_error;
+            cout << "accept, FER=" << error << endl;
+            save_matrix(H.to_tmatrix(), save_filepath);
+        }
+    }
+    return H;
+}
+
+// random start with unseeded rand(), redrawn until H has full row rank (optimize_H.cpp:106-122)
+PermutationsMatrix random_permutation_matrix(int block_size, int n, int m) {
+    for (;;) {
+        TMatrix blocks(n, TCodeword(m));
+        vector<vector<int>> shifts(n, vector<int>(m));
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < m; j++) {
+                blocks[i][j] = rand() % 2;
+                shifts[i][j] = rand() % block_size;
+            }
+        PermutationsMatrix H(block_size, blocks, shifts);
+        if (GetOrtogonal(H.to_tmatrix()).second) return H;
+    }
+}
+
+int main() {
+    std::ios::sync_with_stdio(0);
+    cout.precision(5);
+    cout << fixed;
+
+    const int iters = getenv("LDPC_OPT_ITERS") ? atoi(getenv("LDPC_OPT_ITERS")) : 10000;
+    const string save = getenv("LDPC_OPT_SAVE") ? getenv("LDPC_OPT_SAVE") : "data/optimalH.txt";
+    PermutationsMatrix H0 = getenv("LDPC_OPT_START") ? PermutationsMatrix(20, load_matrix(getenv("LDPC_OPT_START")))
+                                                     : random_permutation_matrix(20, 8, 14);
+    mt19937 rnd(239);
+    TMatrix H = optimize(H0, rnd, iters, save).to_tmatrix();
+
+    cout << FER(H, 10000) << endl;
+    return 0;
+}

@@ -36,7 +36,7 @@ BP_SNR, BP_ITERS = -5.0, 100
 ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
 # algorithmic fp64 instructions per unit of work (DESIGN.md "rooflines"):
 BP_FP64_PER_EDGE_ITER = 48.0          # exp 15 + log-ratio 19 + leave-one-out products 9 + sums 3 + sign/abs 2
-ADMM_FP64_PER_BLOCK_ITER = 54.0       # 12 gather adds + 9 residual + 29 row updates + 3.6 v ops per block
+ADMM_FP64_PER_BLOCK_ITER = 42.0       # 12 gather adds + 9 residual + 17 row updates (4 t, 4 d, 1 zb, 8 fma) + 4 v ops
 
 
 def peaks():
@@ -196,6 +196,7 @@ def run_gpu(args):
     sptr = stream.cuda_stream
     hbm_peak, peak_kind, _ = peaks()
     fp64_peak = L.measure_fp64_peak(local)            # G fp64 FMA instr/s, measured on this GPU
+    smem_peak = L.measure_smem_peak(local)            # GB/s of conflict-free shared-memory loads, measured
 
     def bench_algo(algo, code_name, frames, steps, warmup):
         H = load_rows(code_name)
@@ -296,6 +297,14 @@ def run_gpu(args):
                     "h2d_bytes_per_step": e2e_frames * n * 8, "d2h_bytes_per_step": e2e_frames * (n + 5)},
             "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),
         }
+        if algo == "qpadmm":
+            # the QP-ADMM iteration is bound by shared-memory bandwidth before the FP64 pipe: algorithmic bytes per
+            # frame-iteration = gathers of w (nnz x 8) and v (3 x 8 per block) + stores of w (rows x 8) and v
+            smem_bytes = info["admm_nnz"] * 8 + info["admm_blocks"] * 24 + info["admm_rows"] * 8 + info["admm_n_var"] * 8
+            got = fps_gpu * n_iter * smem_bytes / 1e9
+            res["roofline"]["smem"] = {"achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
+                                       "bytes_per_frame_iter": smem_bytes,
+                                       "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)"}
         code.close()
         return res
 

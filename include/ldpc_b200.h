@@ -175,6 +175,9 @@ int ldpc_host_free(void *ptr);
  * device of `device` (G FMA instructions/s per thread-op, i.e. lanes x clock),
  * used as the denominator of the FP64 roofline in bench.py. */
 int ldpc_measure_fp64_peak(int device, double *gfma_per_s);
+/* ... and the measured shared-memory load bandwidth (GB/s, conflict-free 16-byte loads on all SMs), the
+ * denominator of the shared-memory roofline of the QP-ADMM kernel. */
+int ldpc_measure_smem_peak(int device, double *gbytes_per_s);
 
 /* ---- testing hook: the two fp64 kernels of the BP message update evaluated element-wise on the
  * device (host arrays of `count` doubles): out_exp[i] = exp(-a[i]) for a >= 0, out_log[i] =
