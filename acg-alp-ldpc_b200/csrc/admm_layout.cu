@@ -27,6 +27,7 @@ namespace {
 struct RawBlock {
     int var[3];   // by slot: (last, middle, third) of add_three, qp_admm.h:34-57; -1 = absent
     int nvars, rows;
+    int chain_pos;   // position of the block in its check's chain (0 = first)
 };
 
 struct Layout {
@@ -164,12 +165,12 @@ int compile_admm(ldpc_code *c) {
         const int *idx = c->col_idx.data() + c->row_ptr[r];
         const int d = c->row_ptr[r + 1] - c->row_ptr[r];
         if (d == 0) continue;                                                    // :67-69
-        if (d == 1) { raw.push_back({{idx[0], -1, -1}, 1, 1}); continue; }       // :70-74
-        if (d == 2) { raw.push_back({{idx[0], idx[1], -1}, 2, 2}); continue; }   // :75-83
+        if (d == 1) { raw.push_back({{idx[0], -1, -1}, 1, 1, 0}); continue; }       // :70-74
+        if (d == 2) { raw.push_back({{idx[0], idx[1], -1}, 2, 2, 0}); continue; }   // :75-83
         int last = idx[0];                                                       // :84-91
         for (int j = 1; j <= d - 2; ++j) {
             const int third = (j == d - 2) ? idx[d - 1] : next_aux++;
-            raw.push_back({{last, idx[j], third}, 3, 4});
+            raw.push_back({{last, idx[j], third}, 3, 4, j - 1});
             last = third;
         }
     }
@@ -222,7 +223,12 @@ int compile_admm(ldpc_code *c) {
     std::iota(L.at_v.begin(), L.at_v.end(), 0);
     std::iota(L.at_b.begin(), L.at_b.end(), 0);
     std::stable_sort(L.at_v.begin(), L.at_v.end(), [&](int a, int b) { return L.var_class[a] > L.var_class[b]; });
-    std::stable_sort(L.at_b.begin(), L.at_b.end(), [&](int a, int b) { return L.blk_class[a] < L.blk_class[b]; });
+    // blocks of one class: all first blocks of the chains, then all second blocks, ... -- neighbouring checks of a
+    // quasi-cyclic H touch neighbouring variables, so this keeps consecutive ranks on consecutive banks
+    std::stable_sort(L.at_b.begin(), L.at_b.end(), [&](int a, int b) {
+        if (L.blk_class[a] != L.blk_class[b]) return L.blk_class[a] < L.blk_class[b];
+        return raw[a].chain_pos < raw[b].chain_pos;
+    });
     L.rank_v.resize(nv); L.rank_b.resize(nb);
     for (int r = 0; r < nv; ++r) L.rank_v[L.at_v[r]] = r;
     for (int r = 0; r < nb; ++r) L.rank_b[L.at_b[r]] = r;
