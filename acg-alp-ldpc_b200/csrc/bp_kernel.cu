@@ -322,8 +322,21 @@ static int launch_bp_f(BpParams &p, const ldpc_code *c, int threads, int64_t fra
     return LDPC_OK;
 }
 
+// Decoder::decode / exp() for BP: the likelihood-ratio kernel unless the node degrees would force its message
+// cap below 50 (the reference's own saturation point is ~45.7); LDPC_BP_KERNEL=log|lr overrides (A/B runs).
 int launch_bp(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
               unsigned long long *queue, cudaStream_t stream) {
+    bool lr = bp_lr_cap(c, nullptr) >= 50.0;
+    if (const char *k = getenv("LDPC_BP_KERNEL")) {
+        if (k[0] == 'l' && k[1] == 'o') lr = false;
+        else if (k[0] == 'l' && k[1] == 'r') lr = true;
+    }
+    return lr ? launch_bp_lr(c, fio, frames, var, max_iter, early_exit, queue, stream)
+              : launch_bp_log(c, fio, frames, var, max_iter, early_exit, queue, stream);
+}
+
+int launch_bp_log(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
+                  unsigned long long *queue, cudaStream_t stream) {
     if (frames <= 0) return LDPC_OK;
     if (c->max_row_deg > BP_MAX_DEGREE || c->max_col_deg > BP_MAX_DEGREE)
         return fail(LDPC_E_UNSUPPORTED, "node degree above 64 is not supported by the BP kernel");

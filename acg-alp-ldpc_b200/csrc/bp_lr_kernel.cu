@@ -1,0 +1,500 @@
+// Belief propagation (flooding sum-product) in the likelihood-ratio domain (sm_100a)
+// -- algo/bp.h:155-222, the same schedule and the same function of the inputs as the
+// reference, evaluated without a single transcendental inside the iteration.
+//
+// Algebra.  The reference sends phi(|t|) = -log tanh(|t|/2) and sign(t) from variables to
+// checks and sign * phi(sum phi) back (bp.h:49-57, 77-83).  With L = exp(t):
+//     tanh(t/2) = (L - 1) / (L + 1)
+//     prod_i tanh(t_i/2) = (Pe - Po) / (Pe + Po)
+// where Pe / Po are the sums over all ways of picking the "1" from an even / odd number
+// of the factors (L_i + 1) -- positive terms only, so there is no cancellation at any
+// magnitude -- and the check-to-variable message, as a likelihood ratio, is
+//     x = exp(sign * phi(sum phi)) = (1 + prod tanh) / (1 - prod tanh) = Pe / Po.
+// The variable-to-check message is L_j = L_ch * prod_{k != j} x_k with L_ch = exp(llr),
+// the posterior is L_j * x_j and the hard decision (estimate <= 0, bp.h:193) is
+// posterior <= 1.  Leave-one-out products come from prefix/suffix passes.  Per edge and
+// iteration this is ~13 fp64 instructions (11 of them the Pe/Po recurrences and one
+// division) instead of the ~48 of the exp / log-ratio form (bp_kernel.cu), and every
+// value carries full fp64 relative accuracy, i.e. ~1e-16 absolute in the LLR domain.
+// exp() is evaluated once per variable and frame (L_ch), log() once per variable when a
+// frame's soft output is written.
+//
+// Range.  Messages are clamped to exp(+-C1) on the high word (integer min/max); C1 = 100
+// when the degrees allow it (products of dv-1 / dc-1 messages must stay inside the
+// double range), else smaller; launch_bp falls back to the log-domain kernel when C1
+// would drop below 50 (the reference itself saturates at |t| ~ 45.7).
+//
+// Layout.  A persistent CTA keeps F frames in flight; a lane is a (node, frame) pair with
+// the frame index fastest, and all per-frame arrays are stored [element][frame], so the
+// F lanes of a node read F consecutive doubles: with F = 16 every 64-bit shared-memory
+// access of a half-warp is one conflict-free 128-byte wavefront, whatever the graph.
+//   msg   E x F doubles   C->V likelihood ratios x, overwritten in place by the V->C
+//                         messages L_j (sign bit = hard decision of the variable) and back
+//   lch   n x F doubles   L_ch
+//   dec   n x F bytes     hard decisions of the last variable pass
+//   post  n x F doubles   posterior likelihood ratios (only when soft output is requested)
+// A trip of the main loop is: check pass (which also yields the syndrome of the previous
+// variable pass from the sign bits it loads), barrier, frames that converged or ran out
+// of iterations are published and their slots refilled, variable pass, barrier.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "bpmath.cuh"
+#include "slots.cuh"
+
+namespace ldpc {
+
+constexpr int LR_MAX_DEGREE = 64;
+
+struct BpLrParams {
+    KernelIO io;
+    const uint32_t *rec_v;      // variable records: [var * F * 8, pos_0 * F * 8, ..., pos_{d-1} * F * 8], padded to 4 words
+    const uint32_t *chk_off;    // check rank -> rs * F * 8
+    const BpLrJob *jobs_v, *jobs_c;
+    int rounds_v, rounds_c;
+    int E;
+    int max_iter, early_exit;
+    int clamp_lo, clamp_hi;     // high words of exp(-C1), exp(+C1)
+    double llr_cap;
+    int chunk;                  // frames claimed from the global queue at a time
+    int soft;                   // posterior array present
+};
+
+// control words of a trip, double-buffered by trip parity (written by warp 0 during the
+// variable phase of trip k for trip k+1)
+struct LrCtl {
+    unsigned active;    // slots whose messages are valid V->C messages (they take part in the check pass)
+    unsigned elig;      // slots with iter >= 1 (the reference tests the syndrome from iteration 1 on, bp.h:195)
+    unsigned atmax;     // slots with iter >= max_iter
+    unsigned bad;       // slots with an unsatisfied check (accumulated by the check pass)
+};
+
+template <int F>
+struct LrShared {
+    SlotBlock<F> S;
+    LrCtl ctl[2];
+    unsigned fresh;               // slots whose frame has just been loaded (initial send, bp.h:184)
+    unsigned live;                // slots holding a frame
+    long long q_next, q_end;      // locally claimed range of the global frame queue
+};
+
+__device__ __forceinline__ double ld_f64(const char *p) { return *reinterpret_cast<const double *>(p); }
+__device__ __forceinline__ void st_f64(char *p, double v) { *reinterpret_cast<double *>(p) = v; }
+
+__device__ __forceinline__ double clamp_hi_word(double x, int lo, int hi) {
+    return __hiloint2double(min(max(__double2hiint(x), lo), hi), __double2loint(x));
+}
+
+// ---- variable node of degree D: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
+template <int D, int FB>   // FB = F * 8: byte stride between consecutive elements
+__device__ __forceinline__ void lr_var_update(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
+                                              const uint32_t *rec, int d_runtime, bool fresh, int clamp_lo,
+                                              int clamp_hi) {
+    const int d = D > 0 ? D : d_runtime;
+    constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
+    constexpr int WORDS = D > 0 ? ((D + 1 + 3) / 4) * 4 : 4;
+    uint32_t w[CAP + 4];
+    if (D > 0) {
+#pragma unroll
+        for (int q = 0; q < WORDS / 4; ++q) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rec) + q);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+    } else {
+        for (int q = 0; q <= d; ++q) w[q] = __ldg(rec + q);
+    }
+    const double lc = ld_f64(lch_f + w[0]);
+    double x[CAP], suf[CAP];
+    if (fresh) {                               // all C->V messages are zero (CNode::init, bp.h:42-45): x = 1
+        const double l = clamp_hi_word(lc, clamp_lo, clamp_hi);
+        const int hard = lc <= 1.0 ? (int) 0x80000000 : 0;
+        const double m = __hiloint2double(__double2hiint(l) | hard, __double2loint(l));
+#pragma unroll
+        for (int j = 0; j < d; ++j) st_f64(msg_f + w[1 + j], m);
+        dec_f[w[0] / 8] = (uint8_t) (lc <= 1.0);
+        if (post_f) st_f64(post_f + w[0], lc);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < d; ++j) x[j] = ld_f64(msg_f + w[1 + j]);
+    suf[d - 1] = 1.0;
+#pragma unroll
+    for (int j = d - 2; j >= 0; --j) suf[j] = (j == d - 2) ? x[j + 1] : suf[j + 1] * x[j + 1];
+    double pre = lc;                           // L_ch * prod_{k < j} x_k
+    double lam[CAP];
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        lam[j] = (j == d - 1) ? pre : pre * suf[j];
+        if (j < d - 1) pre *= x[j];
+    }
+    const double tot = lam[d - 1] * x[d - 1];  // posterior likelihood ratio
+    const bool one = tot <= 1.0;               // estimate <= 0 -> bit 1 (bp.h:193)
+    const int hard = one ? (int) 0x80000000 : 0;
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        const int hi = min(max(__double2hiint(lam[j]), clamp_lo), clamp_hi) | hard;
+        st_f64(msg_f + w[1 + j], __hiloint2double(hi, __double2loint(lam[j])));
+    }
+    dec_f[w[0] / 8] = (uint8_t) one;
+    if (post_f) st_f64(post_f + w[0], tot);
+}
+
+// ---- check node of degree D: CNode::message (bp.h:49-57); returns the parity of the decisions
+template <int D, int FB>
+__device__ __forceinline__ int lr_chk_update(char *edge, int d_runtime, int clamp_hi) {
+    const int d = D > 0 ? D : d_runtime;
+    constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
+    double a[CAP], se[CAP], so[CAP];
+    int par = 0;
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        const double m = ld_f64(edge + j * FB);
+        const int hi = __double2hiint(m);
+        par ^= hi;
+        a[j] = __hiloint2double(hi & 0x7fffffff, __double2loint(m));
+    }
+    if (d == 1) {                               // no other variable: phi(0) = +inf in the reference; here the cap
+        st_f64(edge, __hiloint2double(clamp_hi, 0));
+        return (unsigned) par >> 31;
+    }
+    // suffix pairs S_j = (Pe, Po) over the inputs i > j
+    se[d - 1] = 1.0;
+    so[d - 1] = 0.0;
+#pragma unroll
+    for (int j = d - 2; j >= 0; --j) {
+        if (j == d - 2) { se[j] = a[j + 1]; so[j] = 1.0; }
+        else { se[j] = __fma_rn(se[j + 1], a[j + 1], so[j + 1]); so[j] = __fma_rn(so[j + 1], a[j + 1], se[j + 1]); }
+    }
+    double pe = 1.0, po = 0.0;                  // prefix pair over the inputs i < j
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        double ev, od;
+        if (j == 0) { ev = se[0]; od = so[0]; }
+        else if (j == d - 1) { ev = pe; od = po; }
+        else if (j == 1) { ev = __fma_rn(pe, se[j], so[j]); od = __fma_rn(pe, so[j], se[j]); }   // (pe, po) = (a0, 1)
+        else { ev = __fma_rn(pe, se[j], po * so[j]); od = __fma_rn(pe, so[j], po * se[j]); }
+        st_f64(edge + j * FB, div_pos(ev, od));
+        if (j == 0) { pe = a[0]; po = 1.0; }
+        else if (j < d - 1) { const double ne = __fma_rn(pe, a[j], po); po = __fma_rn(po, a[j], pe); pe = ne; }
+    }
+    return (unsigned) par >> 31;
+}
+
+template <int F>
+__global__ void __launch_bounds__(512, 1) bp_lr_kernel(const BpLrParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const KernelIO &io = p.io;
+    const int n = io.n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int warp = tid >> 5, nwarps = nt >> 5, lane = tid & 31;
+    constexpr int FB = F * 8;
+    const int f_lane = lane % F, node_lane = lane / F;
+
+    char *msg = reinterpret_cast<char *>(smem);                          // E x F doubles
+    char *lch = msg + (size_t) p.E * FB;                                 // n x F doubles
+    char *post = lch + (size_t) n * FB;                                  // n x F doubles (soft output only)
+    uint8_t *dec = reinterpret_cast<uint8_t *>(post + (p.soft ? (size_t) n * FB : 0));   // n x F bytes
+    uint8_t *cw = dec + (size_t) n * F;                                  // F x n bytes (experiment mode)
+    LrShared<F> *L = reinterpret_cast<LrShared<F> *>(
+        (reinterpret_cast<uintptr_t>(cw + (io.experiment ? (size_t) n * F : 0)) + 15) & ~(uintptr_t) 15);
+    SlotBlock<F> *S = &L->S;
+
+    slots_init(S);
+    if (tid == 0) {
+        L->ctl[0] = LrCtl{0u, 0u, 0u, 0u};
+        L->ctl[1] = LrCtl{0u, 0u, 0u, 0u};
+        L->fresh = 0u;
+        L->live = 0u;
+        L->q_next = L->q_end = 0;
+        S->alive = F;
+    }
+    __syncthreads();
+
+    char *msg_f = msg + f_lane * 8;
+    const char *lch_f = lch + f_lane * 8;
+    char *post_f = p.soft ? post + f_lane * 8 : nullptr;
+    uint8_t *dec_f = dec + f_lane;
+
+    for (unsigned trip = 0;; ++trip) {
+        LrCtl *ctl = &L->ctl[trip & 1];
+        // ---- check pass (also the syndrome of the previous variable pass)
+        const unsigned active = ctl->active;
+        if (active) {
+            int bad = 0;
+            if ((active >> f_lane) & 1u) {
+                for (int r = 0; r < p.rounds_c; ++r) {
+                    const BpLrJob job = p.jobs_c[r * nwarps + warp];
+                    if (job.degree == 0 || node_lane >= job.count) continue;
+                    char *edge = msg_f + __ldg(p.chk_off + job.first + node_lane);
+                    switch (job.degree) {
+                        case 1: bad |= lr_chk_update<1, FB>(edge, 1, p.clamp_hi); break;
+                        case 2: bad |= lr_chk_update<2, FB>(edge, 2, p.clamp_hi); break;
+                        case 3: bad |= lr_chk_update<3, FB>(edge, 3, p.clamp_hi); break;
+                        case 4: bad |= lr_chk_update<4, FB>(edge, 4, p.clamp_hi); break;
+                        case 5: bad |= lr_chk_update<5, FB>(edge, 5, p.clamp_hi); break;
+                        case 6: bad |= lr_chk_update<6, FB>(edge, 6, p.clamp_hi); break;
+                        case 7: bad |= lr_chk_update<7, FB>(edge, 7, p.clamp_hi); break;
+                        case 8: bad |= lr_chk_update<8, FB>(edge, 8, p.clamp_hi); break;
+                        default: bad |= lr_chk_update<0, FB>(edge, job.degree, p.clamp_hi); break;
+                    }
+                }
+            }
+            unsigned b = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+            for (int s = F; s < 32; s <<= 1) b |= b >> s;      // fold the node lanes: bit f = slot f
+            b &= (F == 32) ? 0xffffffffu : ((1u << F) - 1u);
+            if (lane == 0 && b) atomicOr(&ctl->bad, b);
+        }
+        __syncthreads();
+
+        // ---- publish finished frames, refill their slots
+        const unsigned okmask = ctl->elig & ~ctl->bad & active;          // syndrome vanished (iteration >= 1)
+        const unsigned finmask = (ctl->atmax | (p.early_exit ? okmask : 0u)) & active;
+        if (finmask || trip == 0) {
+            for (int f = 0; f < F; ++f) {
+                if (!((finmask >> f) & 1u)) continue;
+                const int ok = (okmask >> f) & 1u;
+                const uint8_t *df = dec + f;
+                const char *pf = post + f * 8;
+                slot_finish<F>(io, S, f, ok, ok, ok, S->iter[f], cw, [&](int i) { return (int) df[(size_t) i * F]; },
+                               [&](int i) {
+                                   const double t = ld_f64(pf + (size_t) i * FB);
+                                   return log_pos(fmin(fmax(t, 1e-300), 1e300));
+                               });
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // lanes f < F own slot f: empty slots take the next frame of the locally claimed range
+                const unsigned live_before = L->live & ~finmask;
+                const bool want = lane < F && !((live_before >> lane) & 1u) && S->state[lane] != SLOT_DEAD;
+                const unsigned wmask = __ballot_sync(0xffffffffu, want);
+                const int need = __popc(wmask), rank = __popc(wmask & ((1u << lane) - 1u));
+                const long long next = L->q_next, end = L->q_end;
+                __syncwarp();
+                const long long left = end - next;
+                long long got = 0, amt = 0;
+                if (need > left) {                 // claim a new chunk (at least what is missing) from the global queue
+                    amt = max((long long) p.chunk, need - left);
+                    if (lane == 0) got = (long long) atomicAdd(io.queue, (unsigned long long) amt);
+                    got = __shfl_sync(0xffffffffu, got, 0);
+                }
+                if (want) {
+                    const long long fr = rank < left ? next + rank : got + (rank - left);
+                    if (fr < io.frames) { S->frame[lane] = fr; S->iter[lane] = 0; S->hamming[lane] = 0; S->state[lane] = SLOT_NEW; }
+                    else S->state[lane] = SLOT_DEAD;
+                }
+                if (lane == 0) {
+                    if (need > left) { L->q_next = got + (need - left); L->q_end = got + amt; }
+                    else L->q_next = next + need;
+                }
+                __syncwarp();
+                const int st = lane < F ? S->state[lane] : SLOT_DEAD;
+                const unsigned fresh = __ballot_sync(0xffffffffu, st == SLOT_NEW);
+                const unsigned dead = __ballot_sync(0xffffffffu, lane < F && st == SLOT_DEAD);
+                if (lane == 0) {
+                    L->fresh = fresh;
+                    L->live = live_before | fresh;
+                    S->alive = F - __popc(dead);
+                }
+            }
+            __syncthreads();
+            if (S->alive == 0) break;
+            const unsigned fresh = L->fresh;
+            if (fresh) {
+                // L_ch = exp(llr), llr clamped to +-llr_cap; variables without edges keep decision / posterior of the channel
+                slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int f, double l) {
+                    const double lc = exp_signed(fmin(fmax(l, -p.llr_cap), p.llr_cap));
+                    st_f64(lch + (size_t) i * FB + f * 8, lc);
+                    dec[(size_t) i * F + f] = (uint8_t) (lc <= 1.0);
+                    if (p.soft) st_f64(post + (size_t) i * FB + f * 8, lc);
+                });
+            }
+        }
+
+        // ---- variable pass
+        const unsigned live = L->live, fresh = L->fresh;
+        if (warp == 0) {
+            // control words of the next trip
+            int it = 0;
+            if (lane < F && ((live >> lane) & 1u)) {
+                it = ((fresh >> lane) & 1u) ? 0 : S->iter[lane] + 1;
+                S->iter[lane] = it;
+                S->state[lane] = SLOT_ACTIVE;
+            }
+            const unsigned elig = __ballot_sync(0xffffffffu, it >= 1) & live;
+            const unsigned atmax = __ballot_sync(0xffffffffu, it >= p.max_iter) & live;
+            if (lane == 0) L->ctl[(trip + 1) & 1] = LrCtl{live, elig, atmax, 0u};
+        }
+        if ((live >> f_lane) & 1u) {
+            const bool is_fresh = (fresh >> f_lane) & 1u;
+            for (int r = 0; r < p.rounds_v; ++r) {
+                const BpLrJob job = p.jobs_v[r * nwarps + warp];
+                if (job.degree == 0 || node_lane >= job.count) continue;
+                const int stride = ((job.degree + 1 + 3) / 4) * 4;
+                const uint32_t *rec = p.rec_v + job.first + node_lane * stride;
+                switch (job.degree) {
+                    case 1: lr_var_update<1, FB>(msg_f, lch_f, post_f, dec_f, rec, 1, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 2: lr_var_update<2, FB>(msg_f, lch_f, post_f, dec_f, rec, 2, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 3: lr_var_update<3, FB>(msg_f, lch_f, post_f, dec_f, rec, 3, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 4: lr_var_update<4, FB>(msg_f, lch_f, post_f, dec_f, rec, 4, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 5: lr_var_update<5, FB>(msg_f, lch_f, post_f, dec_f, rec, 5, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 6: lr_var_update<6, FB>(msg_f, lch_f, post_f, dec_f, rec, 6, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 7: lr_var_update<7, FB>(msg_f, lch_f, post_f, dec_f, rec, 7, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    case 8: lr_var_update<8, FB>(msg_f, lch_f, post_f, dec_f, rec, 8, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                    default: lr_var_update<0, FB>(msg_f, lch_f, post_f, dec_f, rec, job.degree, is_fresh, p.clamp_lo, p.clamp_hi); break;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && fresh) L->fresh = 0u;      // read again only after the next barrier
+    }
+    slots_flush(io, S);
+}
+
+// ---------------------------------------------------------------- host side
+
+static size_t lr_smem_bytes(const ldpc_code *c, int F, bool soft, bool experiment) {
+    return (size_t) F * 8 * ((size_t) c->E + (size_t) c->n * (soft ? 2 : 1)) + (size_t) F * c->n * (experiment ? 2 : 1) +
+           16 + sizeof(SlotBlock<32>) + 256;
+}
+
+// message cap C1: products of (dv - 1) messages times L_ch, and of (dc - 1) messages, must stay inside the double range
+double bp_lr_cap(const ldpc_code *c, double *llr_cap_out) {
+    const double llr_cap = 100.0;
+    double c1 = 100.0;
+    if (c->max_col_deg > 1) c1 = std::min(c1, (700.0 - llr_cap) / (c->max_col_deg - 1));
+    if (c->max_row_deg > 1) c1 = std::min(c1, (700.0 - 0.7 * c->max_row_deg) / (c->max_row_deg - 1));
+    if (llr_cap_out) *llr_cap_out = llr_cap;
+    return c1;
+}
+
+static std::vector<BpLrJob> make_lr_jobs(const std::vector<BpClass> &classes, const std::vector<uint32_t> &first_of_class,
+                                         int stride_mode, int F, int nwarps, int *rounds) {
+    std::vector<BpLrJob> jobs;
+    const int per_warp = 32 / F;
+    for (size_t k = 0; k < classes.size(); ++k) {
+        const BpClass &cl = classes[k];
+        const int stride = stride_mode ? ((cl.degree + 1 + 3) / 4) * 4 : 1;
+        for (int start = 0; start < cl.count; start += per_warp)
+            jobs.push_back(BpLrJob{(uint16_t) cl.degree, (uint16_t) std::min(per_warp, cl.count - start),
+                                   first_of_class[k] + (uint32_t) start * stride});
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const BpLrJob &a, const BpLrJob &b) { return a.degree > b.degree; });
+    *rounds = ((int) jobs.size() + nwarps - 1) / nwarps;
+    jobs.resize((size_t) *rounds * nwarps, BpLrJob{0, 0, 0});
+    return jobs;
+}
+
+template <typename T>
+static int upload_vec(T **dst, const std::vector<T> &src) {
+    LDPC_CUDA(cudaMalloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *out) {
+    std::lock_guard<std::mutex> lock(c->sched_mu);
+    auto it = c->bp_lr_sched.find({F, nwarps});
+    if (it == c->bp_lr_sched.end()) {
+        BpLrSchedule s;
+        // variable records in rank order (classes of equal degree are adjacent, code.cu)
+        std::vector<uint32_t> rec, first_v, first_c;
+        for (const BpClass &cl : c->var_classes) {
+            first_v.push_back((uint32_t) rec.size());
+            const int stride = ((cl.degree + 1 + 3) / 4) * 4;
+            for (int k = 0; k < cl.count; ++k) {
+                const int v = c->var_order[cl.first + k];
+                const size_t base = rec.size();
+                rec.resize(base + stride, 0u);
+                rec[base] = (uint32_t) v * F * 8;
+                for (int j = 0; j < cl.degree; ++j)
+                    rec[base + 1 + j] = (uint32_t) c->csc_edge[c->col_ptr[v] + j] * F * 8;
+            }
+        }
+        std::vector<uint32_t> chk_off(c->chk_order.size());
+        for (size_t k = 0; k < c->chk_order.size(); ++k) chk_off[k] = (uint32_t) c->row_ptr[c->chk_order[k]] * F * 8;
+        for (const BpClass &cl : c->chk_classes) first_c.push_back((uint32_t) cl.first);
+        std::vector<BpLrJob> jv = make_lr_jobs(c->var_classes, first_v, 1, F, nwarps, &s.rounds_v);
+        std::vector<BpLrJob> jc = make_lr_jobs(c->chk_classes, first_c, 0, F, nwarps, &s.rounds_c);
+        int st;
+        if ((st = upload_vec(&s.rec_v, rec))) return st;
+        if ((st = upload_vec(&s.chk_off, chk_off))) return st;
+        if ((st = upload_vec(&s.jobs_v, jv))) return st;
+        if ((st = upload_vec(&s.jobs_c, jc))) return st;
+        it = c->bp_lr_sched.emplace(std::make_pair(F, nwarps), s).first;
+    }
+    *out = it->second;
+    return LDPC_OK;
+}
+
+template <int F>
+static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
+    BpLrSchedule s;
+    int st = get_lr_schedule(c, F, threads / 32, &s);
+    if (st) return st;
+    p.rec_v = s.rec_v; p.chk_off = s.chk_off; p.jobs_v = s.jobs_v; p.jobs_c = s.jobs_c;
+    p.rounds_v = s.rounds_v; p.rounds_c = s.rounds_c;
+    auto kernel = bp_lr_kernel<F>;
+    LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int per_sm = 0, sms = 0;
+    LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (per_sm < 1) return fail(LDPC_E_UNSUPPORTED, "BP state of this code does not fit on one SM");
+    const long long want = (frames + F - 1) / F;
+    const long long grid = std::min<long long>((long long) per_sm * sms, want);
+    // frames are claimed from the global queue in chunks; small enough that the tail stays balanced
+    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * 4 * F) * F));
+    kernel<<<(unsigned) grid, threads, smem, stream>>>(p);
+    LDPC_CUDA(cudaGetLastError());
+    return LDPC_OK;
+}
+
+int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
+                 unsigned long long *queue, cudaStream_t stream) {
+    if (frames <= 0) return LDPC_OK;
+    BpLrParams p;
+    KernelIO &io = p.io;
+    io.y = fio.y; io.bits = fio.bits; io.ok = fio.ok; io.iters = fio.iters; io.soft = fio.soft;
+    io.experiment = fio.experiment; io.cw_source = fio.cw_source; io.seed = fio.seed;
+    io.frame_begin = fio.frame_begin; io.words = fio.words; io.n_words = fio.n_words;
+    io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
+    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
+    io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
+    p.E = c->E; p.max_iter = max_iter; p.early_exit = early_exit;
+    p.soft = fio.soft != nullptr;
+    const double c1 = bp_lr_cap(c, &p.llr_cap);
+    {
+        const double lo = std::exp(-c1), hi = std::exp(c1);
+        uint64_t blo, bhi;
+        memcpy(&blo, &lo, 8);
+        memcpy(&bhi, &hi, 8);
+        p.clamp_lo = (int) (blo >> 32);
+        p.clamp_hi = (int) (bhi >> 32);
+    }
+    const bool exp_mode = fio.experiment != 0;
+    int F = 16;
+    if (const char *force = getenv("LDPC_BP_F")) {
+        const int v = atoi(force);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) F = v;
+    } else {
+        while (F > 1 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
+    }
+    while (F > 1 && lr_smem_bytes(c, F, p.soft, exp_mode) > 227 * 1024) F >>= 1;
+    const size_t smem = lr_smem_bytes(c, F, p.soft, exp_mode);
+    if (smem > 227 * 1024) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
+    int threads = (long long) c->n * F >= 2048 ? 512 : 256;
+    if (const char *force = getenv("LDPC_BP_THREADS")) {
+        const int v = atoi(force) / 32 * 32;
+        if (v >= 32 && v <= 512) threads = v;
+    }
+    switch (F) {
+        case 16: return launch_lr_f<16>(p, c, threads, smem, frames, stream);
+        case 8: return launch_lr_f<8>(p, c, threads, smem, frames, stream);
+        case 4: return launch_lr_f<4>(p, c, threads, smem, frames, stream);
+        case 2: return launch_lr_f<2>(p, c, threads, smem, frames, stream);
+        default: return launch_lr_f<1>(p, c, threads, smem, frames, stream);
+    }
+}
+
+}  // namespace ldpc

@@ -60,6 +60,23 @@ __device__ __forceinline__ double exp_neg_abs(double t) {
 // exp(-a) for a >= 0
 __device__ __forceinline__ double exp_neg(double a) { return exp_neg_abs(a); }
 
+// exp(t) for |t| <= 700 (no clamp, no abs): same reduction and polynomial as exp_neg_abs
+__device__ __forceinline__ double exp_signed(double t) {
+    const double magic = 6755399441055744.0;                      // 1.5 * 2^52
+    const double a = -t;
+    double kf = __fma_rn(a, K_EXP_RED[0], magic);
+    const int k = __double2loint(kf);
+    kf -= magic;
+    double r = __fma_rn(kf, K_EXP_RED[1], -a);
+    r = __fma_rn(kf, K_EXP_RED[2], r);
+    double p = K_EXP[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = __fma_rn(p, r, K_EXP[i]);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 __device__ __forceinline__ double rcp_fast(double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));        // MUFU.RCP64H, ~2^-23
@@ -98,6 +115,23 @@ __device__ __forceinline__ double log_ratio(double ev, double od) {
     const double u = __fma_rn(two_s, s2 * p, two_s);
     // log(c) rounds to 0x1.62e42fefa39f0p-2 (c is sqrt(2) rounded to double; residual 2.4e-17)
     return __fma_rn((double) d, K_LOG[1], K_LOG[2] + u);
+}
+
+// log(x) for a positive normal x (used once per variable when a frame's soft output is written)
+__device__ __forceinline__ double log_pos(double x) {
+    return x >= 1.0 ? log_ratio(x, 1.0) : -log_ratio(1.0, x);
+}
+
+// a / b for positive normal a, b with b in [2^-1000, 2^1000]: MUFU seed, one Newton step on the
+// reciprocal, quotient, one residual correction (error <= ~1 ulp, no special cases)
+__device__ __forceinline__ double div_pos(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = __fma_rn(-b, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double q = a * r;
+    const double rem = __fma_rn(-b, q, a);
+    return __fma_rn(rem, r, q);
 }
 
 }  // namespace ldpc

@@ -66,7 +66,7 @@ static int compile_bp(ldpc_code *c) {
             classes.back().count++;
         }
     };
-    std::vector<int> chk_order, var_order;
+    std::vector<int> &chk_order = c->chk_order, &var_order = c->var_order;
     rank_by_degree(m, c->row_ptr, chk_order, c->chk_classes);
     rank_by_degree(n, c->col_ptr, var_order, c->var_classes);
     std::vector<uint16_t> chk_rs(chk_order.size());
@@ -166,6 +166,9 @@ void ldpc_code_destroy(ldpc_code_t *c) {
     cudaFree(c->d.blocks); cudaFree(c->d.admm_var); cudaFree(c->d.admm_inc); cudaFree(c->d.admm_var_id); cudaFree(c->d.admm_var_rank);
     cudaFree(c->d.gen_cols);
     for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
+    for (auto &kv : c->bp_lr_sched) {
+        cudaFree(kv.second.rec_v); cudaFree(kv.second.chk_off); cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c);
+    }
     delete c;
 }
 

@@ -42,6 +42,17 @@ struct BpJob {        // the work of one warp in one round: node ranks [first, f
     uint16_t pad;
 };
 struct BpClass { int degree, first, count; };
+// likelihood-ratio BP kernel (bp_lr_kernel.cu): tables depend on the frames per CTA (byte offsets are pre-scaled)
+struct BpLrJob {      // the work of one warp in one round: `count` nodes of one degree x F frames
+    uint16_t degree;  // 0 = nothing to do
+    uint16_t count;
+    uint32_t first;   // variable pass: word offset of the first node record; check pass: first check rank
+};
+struct BpLrSchedule {
+    uint32_t *rec_v = nullptr, *chk_off = nullptr;
+    BpLrJob *jobs_v = nullptr, *jobs_c = nullptr;
+    int rounds_v = 0, rounds_c = 0;
+};
 struct BpSchedule {   // device arrays, rounds x warps jobs each
     BpJob *jobs_v = nullptr, *jobs_c = nullptr;
     int rounds_v = 0, rounds_c = 0;
@@ -97,10 +108,12 @@ struct ldpc_code {
     // host copies (also used by tests through ldpc_code_info)
     std::vector<int> row_ptr, col_idx, col_ptr, csc_edge;
     std::vector<ldpc::BpClass> chk_classes, var_classes;   // nodes of equal degree are adjacent in rank order
+    std::vector<int> chk_order, var_order;                 // rank -> node index (degree-0 nodes dropped)
     ldpc::DeviceTables d;
     // BP launch schedules, built on first use per (frames per CTA, warps per CTA)
     mutable std::mutex sched_mu;
     mutable std::map<std::pair<int, int>, ldpc::BpSchedule> bp_sched;
+    mutable std::map<std::pair<int, int>, ldpc::BpLrSchedule> bp_lr_sched;
 };
 
 namespace ldpc {
@@ -126,6 +139,12 @@ int compile_admm(ldpc_code *code);
 
 int launch_bp(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
               int early_exit, unsigned long long *queue, cudaStream_t stream);
+// the two BP kernels behind launch_bp: likelihood-ratio domain (default) and log domain (large node degrees)
+int launch_bp_lr(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
+                 int early_exit, unsigned long long *queue, cudaStream_t stream);
+int launch_bp_log(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
+                  int early_exit, unsigned long long *queue, cudaStream_t stream);
+double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
 int launch_channel(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames, double sigma,

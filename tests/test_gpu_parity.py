@@ -231,9 +231,10 @@ def test_irregular_code_special_blocks(gpu_lib, oracle):
     assert (gb == ob).all() and (gok == ook).all() and (git == oit).all()
     fin = np.isfinite(opost) & (ook == 1)[:, None]
     assert np.allclose(gpost[fin], opost[fin], rtol=1e-4, atol=0)
-    # degree-1 checks pin a bit: the reference's LLR is +inf, the kernel caps magnitudes near 700
+    # degree-1 checks pin a bit: the reference's LLR is +inf, the kernels cap message magnitudes (100 in the
+    # likelihood-ratio kernel, ~700 in the log-domain one)
     pinned = np.isinf(opost) & (ook == 1)[:, None]
-    assert pinned.any() and (gpost[pinned] > 600).all()
+    assert pinned.any() and (gpost[pinned] > 90).all()
 
 
 def test_experiment_counters_match_oracle(gpu_lib, codes, oracle):
