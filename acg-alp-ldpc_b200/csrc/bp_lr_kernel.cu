@@ -50,9 +50,8 @@ constexpr int LR_MAX_DEGREE = 64;
 struct BpLrParams {
     KernelIO io;
     const uint32_t *rec_v;      // variable records: [var * F * 8, pos_0 * F * 8, ..., pos_{d-1} * F * 8], padded to 4 words
-    const uint32_t *chk_off;    // check rank -> rs * F * 8
-    const BpLrJob *jobs_v, *jobs_c;
-    int rounds_v, rounds_c;
+    const BpLrRun *runs_v, *runs_c;   // per warp: max_runs entries, terminated by degree 0
+    int max_runs_v, max_runs_c;
     int E;
     int max_iter, early_exit;
     int clamp_lo, clamp_hi;     // high words of exp(-C1), exp(+C1)
@@ -86,36 +85,34 @@ __device__ __forceinline__ double clamp_hi_word(double x, int lo, int hi) {
     return __hiloint2double(min(max(__double2hiint(x), lo), hi), __double2loint(x));
 }
 
+// node record of a variable of degree D: word 0 = var * F * 8, words 1..D = message slot * F * 8
+template <int D>
+struct LrRec {
+    static constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
+    static constexpr int WORDS = D > 0 ? ((D + 1 + 3) / 4) * 4 : 4;
+    uint32_t w[CAP + 4];
+    __device__ __forceinline__ void load(const uint32_t *rec, int d) {
+        if (D > 0) {
+#pragma unroll
+            for (int q = 0; q < WORDS / 4; ++q) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rec) + q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+        } else {
+            for (int q = 0; q <= d; ++q) w[q] = __ldg(rec + q);
+        }
+    }
+};
+
 // ---- variable node of degree D: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
-template <int D, int FB>   // FB = F * 8: byte stride between consecutive elements
+template <int D, int FB, bool SOFT>   // FB = F * 8: byte stride between consecutive elements
 __device__ __forceinline__ void lr_var_update(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
-                                              const uint32_t *rec, int d_runtime, bool fresh, int clamp_lo,
-                                              int clamp_hi) {
+                                              const LrRec<D> &r, int d_runtime, int clamp_lo, int clamp_hi) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
-    constexpr int WORDS = D > 0 ? ((D + 1 + 3) / 4) * 4 : 4;
-    uint32_t w[CAP + 4];
-    if (D > 0) {
-#pragma unroll
-        for (int q = 0; q < WORDS / 4; ++q) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rec) + q);
-            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
-    } else {
-        for (int q = 0; q <= d; ++q) w[q] = __ldg(rec + q);
-    }
+    const uint32_t *w = r.w;
     const double lc = ld_f64(lch_f + w[0]);
     double x[CAP], suf[CAP];
-    if (fresh) {                               // all C->V messages are zero (CNode::init, bp.h:42-45): x = 1
-        const double l = clamp_hi_word(lc, clamp_lo, clamp_hi);
-        const int hard = lc <= 1.0 ? (int) 0x80000000 : 0;
-        const double m = __hiloint2double(__double2hiint(l) | hard, __double2loint(l));
-#pragma unroll
-        for (int j = 0; j < d; ++j) st_f64(msg_f + w[1 + j], m);
-        dec_f[w[0] / 8] = (uint8_t) (lc <= 1.0);
-        if (post_f) st_f64(post_f + w[0], lc);
-        return;
-    }
 #pragma unroll
     for (int j = 0; j < d; ++j) x[j] = ld_f64(msg_f + w[1 + j]);
     suf[d - 1] = 1.0;
@@ -137,7 +134,35 @@ __device__ __forceinline__ void lr_var_update(char *msg_f, const char *lch_f, ch
         st_f64(msg_f + w[1 + j], __hiloint2double(hi, __double2loint(lam[j])));
     }
     dec_f[w[0] / 8] = (uint8_t) one;
-    if (post_f) st_f64(post_f + w[0], tot);
+    if (SOFT) st_f64(post_f + w[0], tot);
+}
+
+// the initial send (bp.h:184): all C->V messages are zero (CNode::init, bp.h:42-45), i.e. x = 1
+template <int D, int FB, bool SOFT>
+__device__ __forceinline__ void lr_var_first(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
+                                             const LrRec<D> &r, int d_runtime, int clamp_lo, int clamp_hi) {
+    const int d = D > 0 ? D : d_runtime;
+    const uint32_t *w = r.w;
+    const double lc = ld_f64(lch_f + w[0]);
+    const double l = clamp_hi_word(lc, clamp_lo, clamp_hi);
+    const int hard = lc <= 1.0 ? (int) 0x80000000 : 0;
+    const double m = __hiloint2double(__double2hiint(l) | hard, __double2loint(l));
+#pragma unroll
+    for (int j = 0; j < d; ++j) st_f64(msg_f + w[1 + j], m);
+    dec_f[w[0] / 8] = (uint8_t) (lc <= 1.0);
+    if (SOFT) st_f64(post_f + w[0], lc);
+}
+
+// one step of the variable pass: 32/F consecutive ranks of degree D, one per lane group
+template <int D, int F, bool SOFT>
+__device__ __forceinline__ void lr_var_step(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
+                                            const uint32_t *rec, int degree, int node_lane, bool fresh,
+                                            int clamp_lo, int clamp_hi) {
+    const int stride = D > 0 ? ((D + 1 + 3) / 4) * 4 : ((degree + 1 + 3) / 4) * 4;
+    LrRec<D> r;
+    r.load(rec + node_lane * stride, degree);
+    if (fresh) lr_var_first<D, F * 8, SOFT>(msg_f, lch_f, post_f, dec_f, r, degree, clamp_lo, clamp_hi);
+    else lr_var_update<D, F * 8, SOFT>(msg_f, lch_f, post_f, dec_f, r, degree, clamp_lo, clamp_hi);
 }
 
 // ---- check node of degree D: CNode::message (bp.h:49-57); returns the parity of the decisions
@@ -181,8 +206,8 @@ __device__ __forceinline__ int lr_chk_update(char *edge, int d_runtime, int clam
     return (unsigned) par >> 31;
 }
 
-template <int F>
-__global__ void __launch_bounds__(512, 1) bp_lr_kernel(const BpLrParams p) {
+template <int F, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
     const int n = io.n;
@@ -213,7 +238,11 @@ __global__ void __launch_bounds__(512, 1) bp_lr_kernel(const BpLrParams p) {
 
     char *msg_f = msg + f_lane * 8;
     const char *lch_f = lch + f_lane * 8;
-    char *post_f = p.soft ? post + f_lane * 8 : nullptr;
+    char *post_f = post + f_lane * 8;
+    const bool soft = p.soft != 0;
+    // this warp's steps of the two passes, heaviest degree first, terminated by degree 0
+    const BpLrRun *my_steps_v = p.runs_v + (size_t) warp * p.max_runs_v;
+    const BpLrRun *my_steps_c = p.runs_c + (size_t) warp * p.max_runs_c;
     uint8_t *dec_f = dec + f_lane;
 
     for (unsigned trip = 0;; ++trip) {
@@ -223,22 +252,23 @@ __global__ void __launch_bounds__(512, 1) bp_lr_kernel(const BpLrParams p) {
         if (active) {
             int bad = 0;
             if ((active >> f_lane) & 1u) {
-                for (int r = 0; r < p.rounds_c; ++r) {
-                    const BpLrJob job = p.jobs_c[r * nwarps + warp];
-                    if (job.degree == 0 || node_lane >= job.count) continue;
-                    char *edge = msg_f + __ldg(p.chk_off + job.first + node_lane);
-                    switch (job.degree) {
-                        case 1: bad |= lr_chk_update<1, FB>(edge, 1, p.clamp_hi); break;
-                        case 2: bad |= lr_chk_update<2, FB>(edge, 2, p.clamp_hi); break;
-                        case 3: bad |= lr_chk_update<3, FB>(edge, 3, p.clamp_hi); break;
-                        case 4: bad |= lr_chk_update<4, FB>(edge, 4, p.clamp_hi); break;
-                        case 5: bad |= lr_chk_update<5, FB>(edge, 5, p.clamp_hi); break;
-                        case 6: bad |= lr_chk_update<6, FB>(edge, 6, p.clamp_hi); break;
-                        case 7: bad |= lr_chk_update<7, FB>(edge, 7, p.clamp_hi); break;
-                        case 8: bad |= lr_chk_update<8, FB>(edge, 8, p.clamp_hi); break;
-                        default: bad |= lr_chk_update<0, FB>(edge, job.degree, p.clamp_hi); break;
-                    }
+                const BpLrRun *q = my_steps_c;
+                BpLrRun e = *q;
+                while (e.degree > 8) {
+                    const BpLrRun nx = *++q;
+                    if (node_lane < e.nodes)
+                        bad |= lr_chk_update<0, FB>(msg_f + e.first + node_lane * e.degree * FB, e.degree, p.clamp_hi);
+                    e = nx;
                 }
+#define LDPC_CHK_STEPS(D)                                                                                   \
+    while (e.degree == D) {                                                                                 \
+        const BpLrRun nx = *++q;                                                                            \
+        if (node_lane < e.nodes) bad |= lr_chk_update<D, FB>(msg_f + e.first + node_lane * D * FB, D, p.clamp_hi); \
+        e = nx;                                                                                             \
+    }
+                LDPC_CHK_STEPS(8) LDPC_CHK_STEPS(7) LDPC_CHK_STEPS(6) LDPC_CHK_STEPS(5)
+                LDPC_CHK_STEPS(4) LDPC_CHK_STEPS(3) LDPC_CHK_STEPS(2) LDPC_CHK_STEPS(1)
+#undef LDPC_CHK_STEPS
             }
             unsigned b = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
@@ -328,23 +358,29 @@ __global__ void __launch_bounds__(512, 1) bp_lr_kernel(const BpLrParams p) {
         }
         if ((live >> f_lane) & 1u) {
             const bool is_fresh = (fresh >> f_lane) & 1u;
-            for (int r = 0; r < p.rounds_v; ++r) {
-                const BpLrJob job = p.jobs_v[r * nwarps + warp];
-                if (job.degree == 0 || node_lane >= job.count) continue;
-                const int stride = ((job.degree + 1 + 3) / 4) * 4;
-                const uint32_t *rec = p.rec_v + job.first + node_lane * stride;
-                switch (job.degree) {
-                    case 1: lr_var_update<1, FB>(msg_f, lch_f, post_f, dec_f, rec, 1, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 2: lr_var_update<2, FB>(msg_f, lch_f, post_f, dec_f, rec, 2, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 3: lr_var_update<3, FB>(msg_f, lch_f, post_f, dec_f, rec, 3, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 4: lr_var_update<4, FB>(msg_f, lch_f, post_f, dec_f, rec, 4, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 5: lr_var_update<5, FB>(msg_f, lch_f, post_f, dec_f, rec, 5, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 6: lr_var_update<6, FB>(msg_f, lch_f, post_f, dec_f, rec, 6, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 7: lr_var_update<7, FB>(msg_f, lch_f, post_f, dec_f, rec, 7, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    case 8: lr_var_update<8, FB>(msg_f, lch_f, post_f, dec_f, rec, 8, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                    default: lr_var_update<0, FB>(msg_f, lch_f, post_f, dec_f, rec, job.degree, is_fresh, p.clamp_lo, p.clamp_hi); break;
-                }
-            }
+            const BpLrRun *q = my_steps_v;
+            BpLrRun e = *q;
+#define LDPC_VAR_STEP(D)                                                                                          \
+    do {                                                                                                          \
+        const BpLrRun nx = *++q;                                                                                  \
+        if (node_lane < e.nodes) {                                                                                \
+            if (soft) lr_var_step<D, F, true>(msg_f, lch_f, post_f, dec_f, p.rec_v + e.first, e.degree, node_lane, \
+                                              is_fresh, p.clamp_lo, p.clamp_hi);                                  \
+            else lr_var_step<D, F, false>(msg_f, lch_f, post_f, dec_f, p.rec_v + e.first, e.degree, node_lane,    \
+                                          is_fresh, p.clamp_lo, p.clamp_hi);                                      \
+        }                                                                                                         \
+        e = nx;                                                                                                   \
+    } while (0)
+            while (e.degree > 8) LDPC_VAR_STEP(0);
+            while (e.degree == 8) LDPC_VAR_STEP(8);
+            while (e.degree == 7) LDPC_VAR_STEP(7);
+            while (e.degree == 6) LDPC_VAR_STEP(6);
+            while (e.degree == 5) LDPC_VAR_STEP(5);
+            while (e.degree == 4) LDPC_VAR_STEP(4);
+            while (e.degree == 3) LDPC_VAR_STEP(3);
+            while (e.degree == 2) LDPC_VAR_STEP(2);
+            while (e.degree == 1) LDPC_VAR_STEP(1);
+#undef LDPC_VAR_STEP
         }
         __syncthreads();
         if (tid == 0 && fresh) L->fresh = 0u;      // read again only after the next barrier
@@ -369,21 +405,28 @@ double bp_lr_cap(const ldpc_code *c, double *llr_cap_out) {
     return c1;
 }
 
-static std::vector<BpLrJob> make_lr_jobs(const std::vector<BpClass> &classes, const std::vector<uint32_t> &first_of_class,
-                                         int stride_mode, int F, int nwarps, int *rounds) {
-    std::vector<BpLrJob> jobs;
-    const int per_warp = 32 / F;
-    for (size_t k = 0; k < classes.size(); ++k) {
-        const BpClass &cl = classes[k];
-        const int stride = stride_mode ? ((cl.degree + 1 + 3) / 4) * 4 : 1;
-        for (int start = 0; start < cl.count; start += per_warp)
-            jobs.push_back(BpLrJob{(uint16_t) cl.degree, (uint16_t) std::min(per_warp, cl.count - start),
-                                   first_of_class[k] + (uint32_t) start * stride});
-    }
-    std::stable_sort(jobs.begin(), jobs.end(), [](const BpLrJob &a, const BpLrJob &b) { return a.degree > b.degree; });
-    *rounds = ((int) jobs.size() + nwarps - 1) / nwarps;
-    jobs.resize((size_t) *rounds * nwarps, BpLrJob{0, 0, 0});
-    return jobs;
+// Deals the steps (32/F consecutive node ranks of one degree class = one node per lane group) to the warps
+// round-robin, heaviest classes first, so the warps of a pass finish together.  Per warp: its steps in that
+// order, terminated by a degree-0 entry.
+template <typename FirstOf>
+static std::vector<BpLrRun> make_runs(const std::vector<BpClass> &classes, int F, int nwarps, int *max_runs,
+                                      FirstOf first_of) {
+    const int G = 32 / F;
+    std::vector<int> order(classes.size());
+    for (size_t k = 0; k < classes.size(); ++k) order[k] = (int) k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return classes[a].degree > classes[b].degree; });
+    std::vector<std::vector<BpLrRun>> per_warp(nwarps);
+    int s_global = 0;
+    for (int k : order)
+        for (int n0 = 0; n0 < classes[k].count; n0 += G, ++s_global)
+            per_warp[s_global % nwarps].push_back(BpLrRun{(uint16_t) classes[k].degree,
+                                                          (uint16_t) std::min(G, classes[k].count - n0), first_of(k, n0)});
+    size_t mr = 1;
+    for (auto &rw : per_warp) mr = std::max(mr, rw.size() + 1);
+    std::vector<BpLrRun> flat((size_t) nwarps * mr, BpLrRun{0, 0, 0});
+    for (int w = 0; w < nwarps; ++w) std::copy(per_warp[w].begin(), per_warp[w].end(), flat.begin() + (size_t) w * mr);
+    *max_runs = (int) mr;
+    return flat;
 }
 
 template <typename T>
@@ -398,8 +441,20 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
     auto it = c->bp_lr_sched.find({F, nwarps});
     if (it == c->bp_lr_sched.end()) {
         BpLrSchedule s;
+        // message slots in check-rank order: the checks of one degree class are stored back to back
+        std::vector<int> slot_of_edge(c->E, 0), class_slot0;
+        {
+            int slot = 0;
+            for (const BpClass &cl : c->chk_classes) {
+                class_slot0.push_back(slot);
+                for (int k = 0; k < cl.count; ++k) {
+                    const int chk = c->chk_order[cl.first + k];
+                    for (int e = c->row_ptr[chk]; e < c->row_ptr[chk + 1]; ++e) slot_of_edge[e] = slot++;
+                }
+            }
+        }
         // variable records in rank order (classes of equal degree are adjacent, code.cu)
-        std::vector<uint32_t> rec, first_v, first_c;
+        std::vector<uint32_t> rec, first_v;
         for (const BpClass &cl : c->var_classes) {
             first_v.push_back((uint32_t) rec.size());
             const int stride = ((cl.degree + 1 + 3) / 4) * 4;
@@ -409,33 +464,33 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                 rec.resize(base + stride, 0u);
                 rec[base] = (uint32_t) v * F * 8;
                 for (int j = 0; j < cl.degree; ++j)
-                    rec[base + 1 + j] = (uint32_t) c->csc_edge[c->col_ptr[v] + j] * F * 8;
+                    rec[base + 1 + j] = (uint32_t) slot_of_edge[c->csc_edge[c->col_ptr[v] + j]] * F * 8;
             }
         }
-        std::vector<uint32_t> chk_off(c->chk_order.size());
-        for (size_t k = 0; k < c->chk_order.size(); ++k) chk_off[k] = (uint32_t) c->row_ptr[c->chk_order[k]] * F * 8;
-        for (const BpClass &cl : c->chk_classes) first_c.push_back((uint32_t) cl.first);
-        std::vector<BpLrJob> jv = make_lr_jobs(c->var_classes, first_v, 1, F, nwarps, &s.rounds_v);
-        std::vector<BpLrJob> jc = make_lr_jobs(c->chk_classes, first_c, 0, F, nwarps, &s.rounds_c);
+        std::vector<BpLrRun> rv = make_runs(c->var_classes, F, nwarps, &s.max_runs_v, [&](int cls, int node0) {
+            return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 4);
+        });
+        std::vector<BpLrRun> rc = make_runs(c->chk_classes, F, nwarps, &s.max_runs_c, [&](int cls, int node0) {
+            return (uint32_t) (class_slot0[cls] + node0 * c->chk_classes[cls].degree) * F * 8;
+        });
         int st;
         if ((st = upload_vec(&s.rec_v, rec))) return st;
-        if ((st = upload_vec(&s.chk_off, chk_off))) return st;
-        if ((st = upload_vec(&s.jobs_v, jv))) return st;
-        if ((st = upload_vec(&s.jobs_c, jc))) return st;
+        if ((st = upload_vec(&s.runs_v, rv))) return st;
+        if ((st = upload_vec(&s.runs_c, rc))) return st;
         it = c->bp_lr_sched.emplace(std::make_pair(F, nwarps), s).first;
     }
     *out = it->second;
     return LDPC_OK;
 }
 
-template <int F>
-static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
+template <int F, int MAXT>
+static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
     BpLrSchedule s;
     int st = get_lr_schedule(c, F, threads / 32, &s);
     if (st) return st;
-    p.rec_v = s.rec_v; p.chk_off = s.chk_off; p.jobs_v = s.jobs_v; p.jobs_c = s.jobs_c;
-    p.rounds_v = s.rounds_v; p.rounds_c = s.rounds_c;
-    auto kernel = bp_lr_kernel<F>;
+    p.rec_v = s.rec_v; p.runs_v = s.runs_v; p.runs_c = s.runs_c;
+    p.max_runs_v = s.max_runs_v; p.max_runs_c = s.max_runs_c;
+    auto kernel = bp_lr_kernel<F, MAXT>;
     LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
@@ -448,6 +503,14 @@ static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, size_t sm
     kernel<<<(unsigned) grid, threads, smem, stream>>>(p);
     LDPC_CUDA(cudaGetLastError());
     return LDPC_OK;
+}
+
+// register budget by CTA size: 128 / 85 / 64 registers per thread
+template <int F>
+static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
+    if (threads <= 512) return launch_lr_ft<F, 512>(p, c, threads, smem, frames, stream);
+    if (threads <= 768) return launch_lr_ft<F, 768>(p, c, threads, smem, frames, stream);
+    return launch_lr_ft<F, 1024>(p, c, threads, smem, frames, stream);
 }
 
 int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
@@ -486,7 +549,7 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     int threads = (long long) c->n * F >= 2048 ? 512 : 256;
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
-        if (v >= 32 && v <= 512) threads = v;
+        if (v >= 32 && v <= 1024) threads = v;
     }
     switch (F) {
         case 16: return launch_lr_f<16>(p, c, threads, smem, frames, stream);

@@ -42,20 +42,21 @@ struct BpJob {        // the work of one warp in one round: node ranks [first, f
     uint16_t pad;
 };
 struct BpClass { int degree, first, count; };
-// likelihood-ratio BP kernel (bp_lr_kernel.cu): tables depend on the frames per CTA (byte offsets are pre-scaled)
-struct BpLrJob {      // the work of one warp in one round: `count` nodes of one degree x F frames
-    uint16_t degree;  // 0 = nothing to do
-    uint16_t count;
-    uint32_t first;   // variable pass: word offset of the first node record; check pass: first check rank
-};
-struct BpLrSchedule {
-    uint32_t *rec_v = nullptr, *chk_off = nullptr;
-    BpLrJob *jobs_v = nullptr, *jobs_c = nullptr;
-    int rounds_v = 0, rounds_c = 0;
-};
-struct BpSchedule {   // device arrays, rounds x warps jobs each
+struct BpSchedule {   // device arrays, rounds x warps jobs each (log-domain kernel)
     BpJob *jobs_v = nullptr, *jobs_c = nullptr;
     int rounds_v = 0, rounds_c = 0;
+};
+// likelihood-ratio BP kernel (bp_lr_kernel.cu): tables depend on the frames per CTA (byte offsets are pre-scaled)
+struct alignas(8) BpLrRun {   // consecutive node ranks of one degree, processed by one warp (32/F nodes per step)
+    uint16_t degree;          // 0 = end of the warp's list
+    uint16_t nodes;
+    uint32_t first;           // variable pass: word offset of the first node record; check pass: byte offset of
+                              // the first message of the first node
+};
+struct BpLrSchedule {
+    uint32_t *rec_v = nullptr;
+    BpLrRun *runs_v = nullptr, *runs_c = nullptr;
+    int max_runs_v = 0, max_runs_c = 0;
 };
 
 // QP-ADMM works per BLOCK: one three-variable check of the chain decomposition
