@@ -331,8 +331,11 @@ int launch_bp(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var
         if (k[0] == 'l' && k[1] == 'o') lr = false;
         else if (k[0] == 'l' && k[1] == 'r') lr = true;
     }
-    return lr ? launch_bp_lr(c, fio, frames, var, max_iter, early_exit, queue, stream)
-              : launch_bp_log(c, fio, frames, var, max_iter, early_exit, queue, stream);
+    if (lr) {
+        const int st = launch_bp_lr(c, fio, frames, var, max_iter, early_exit, queue, stream);
+        if (st != LDPC_E_UNSUPPORTED) return st;      // codes beyond its shared-memory layout take the log-domain kernel
+    }
+    return launch_bp_log(c, fio, frames, var, max_iter, early_exit, queue, stream);
 }
 
 int launch_bp_log(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,

@@ -24,10 +24,13 @@
 // double range), else smaller; launch_bp falls back to the log-domain kernel when C1
 // would drop below 50 (the reference itself saturates at |t| ~ 45.7).
 //
-// Layout.  A persistent CTA keeps F frames in flight; a lane is a (node, frame) pair with
-// the frame index fastest, and all per-frame arrays are stored [element][frame], so the
-// F lanes of a node read F consecutive doubles: with F = 16 every 64-bit shared-memory
-// access of a half-warp is one conflict-free 128-byte wavefront, whatever the graph.
+// Layout.  A persistent CTA keeps F frames in flight; a lane is a (node, frame PAIR) and all
+// per-frame arrays are stored [element][frame] with the frame index fastest, so a lane moves
+// its two frames with one 128-bit access and the F/2 lanes of a node cover F consecutive
+// doubles: with F = 16 every quarter-warp access is one conflict-free 128-byte wavefront,
+// whatever the graph.  Two frames per lane halve the address arithmetic, the shared-memory
+// instructions and the per-node bookkeeping per frame and give every thread two independent
+// dependency chains.
 //   msg   E x F doubles   C->V likelihood ratios x, overwritten in place by the V->C
 //                         messages L_j (sign bit = hard decision of the variable) and back
 //   lch   n x F doubles   L_ch
@@ -39,6 +42,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "bpmath.cuh"
 #include "slots.cuh"
@@ -49,9 +53,10 @@ constexpr int LR_MAX_DEGREE = 64;
 
 struct BpLrParams {
     KernelIO io;
-    const uint32_t *rec_v;      // variable records: [var * F * 8, pos_0 * F * 8, ..., pos_{d-1} * F * 8], padded to 4 words
-    const BpLrRun *runs_v, *runs_c;   // per warp: max_runs entries, terminated by degree 0
-    int max_runs_v, max_runs_c;
+    const uint32_t *rec_v;      // variable records (words): [var * F * 8, slot_0 * F * 8, ..., slot_{d-1} * F * 8], padded to 4 words
+    const uint32_t *steps;      // per warp: steps_per_warp words, variable pass then check pass, each list ends with 0
+    int rec_words;              // total words of rec_v
+    int steps_per_warp, steps_c_off;
     int E;
     int max_iter, early_exit;
     int clamp_lo, clamp_hi;     // high words of exp(-C1), exp(+C1)
@@ -59,6 +64,15 @@ struct BpLrParams {
     int chunk;                  // frames claimed from the global queue at a time
     int soft;                   // posterior array present
 };
+
+// A step = one warp instruction's worth of nodes of one degree: 64/F consecutive ranks, one per lane group.
+//   bits 0-17  byte offset (variable pass: of the first node record in the shared record table;
+//              check pass: of the first message of the first node)
+//   bits 18-22 nodes in the step - 1
+//   bits 23-29 degree (0 = end of list)
+__host__ __device__ __forceinline__ uint32_t lr_step_word(uint32_t first, int nodes, int degree) {
+    return first | ((uint32_t) (nodes - 1) << 18) | ((uint32_t) degree << 23);
+}
 
 // control words of a trip, double-buffered by trip parity (written by warp 0 during the
 // variable phase of trip k for trip k+1)
@@ -81,129 +95,107 @@ struct LrShared {
 __device__ __forceinline__ double ld_f64(const char *p) { return *reinterpret_cast<const double *>(p); }
 __device__ __forceinline__ void st_f64(char *p, double v) { *reinterpret_cast<double *>(p) = v; }
 
-__device__ __forceinline__ double clamp_hi_word(double x, int lo, int hi) {
-    return __hiloint2double(min(max(__double2hiint(x), lo), hi), __double2loint(x));
+// two frames of one element
+struct P2 {
+    double a, b;
+};
+__device__ __forceinline__ P2 ld_p2(const char *p) {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    return P2{t.x, t.y};
+}
+__device__ __forceinline__ void st_p2(char *p, P2 v) { *reinterpret_cast<double2 *>(p) = make_double2(v.a, v.b); }
+__device__ __forceinline__ P2 operator*(P2 x, P2 y) { return P2{x.a * y.a, x.b * y.b}; }
+__device__ __forceinline__ P2 fma2(P2 x, P2 y, P2 z) { return P2{__fma_rn(x.a, y.a, z.a), __fma_rn(x.b, y.b, z.b)}; }
+__device__ __forceinline__ P2 div2(P2 x, P2 y) { return P2{div_pos(x.a, y.a), div_pos(x.b, y.b)}; }
+
+// clamp to [exp(-C1), exp(C1)] on the high word and put the variable's decision into the sign bit
+__device__ __forceinline__ double clamp_sign(double x, int lo, int hi, int sign) {
+    return __hiloint2double(min(max(__double2hiint(x), lo), hi) | sign, __double2loint(x));
 }
 
-// node record of a variable of degree D: word 0 = var * F * 8, words 1..D = message slot * F * 8
-template <int D>
-struct LrRec {
-    static constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
-    static constexpr int WORDS = D > 0 ? ((D + 1 + 3) / 4) * 4 : 4;
-    uint32_t w[CAP + 4];
-    __device__ __forceinline__ void load(const uint32_t *rec, int d) {
-        if (D > 0) {
-#pragma unroll
-            for (int q = 0; q < WORDS / 4; ++q) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rec) + q);
-                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-            }
-        } else {
-            for (int q = 0; q <= d; ++q) w[q] = __ldg(rec + q);
-        }
-    }
-};
-
-// ---- variable node of degree D: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
-template <int D, int FB, bool SOFT>   // FB = F * 8: byte stride between consecutive elements
-__device__ __forceinline__ void lr_var_update(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
-                                              const LrRec<D> &r, int d_runtime, int clamp_lo, int clamp_hi) {
+// ---- variable node of degree D, two frames: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
+// rec = the node's record in shared memory; msg_p / lch_p / post_p / dec_p already point at the lane's frame pair.
+template <int D, bool SOFT>
+__device__ __forceinline__ void lr_var_update(char *msg_p, const char *lch_p, char *post_p, uint8_t *dec_p,
+                                              const uint32_t *rec, int d_runtime, int clamp_lo, int clamp_hi) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
-    const uint32_t *w = r.w;
-    const double lc = ld_f64(lch_f + w[0]);
-    double x[CAP], suf[CAP];
+    uint32_t w[CAP + 4];
+    if (D > 0) {
 #pragma unroll
-    for (int j = 0; j < d; ++j) x[j] = ld_f64(msg_f + w[1 + j]);
-    suf[d - 1] = 1.0;
+        for (int q = 0; q < (D + 1 + 3) / 4; ++q) {
+            const uint4 t = *(reinterpret_cast<const uint4 *>(rec) + q);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+    } else {
+        for (int q = 0; q <= d; ++q) w[q] = rec[q];
+    }
+    const P2 lc = ld_p2(lch_p + w[0]);
+    P2 x[CAP], suf[CAP], lam[CAP];
+#pragma unroll
+    for (int j = 0; j < d; ++j) x[j] = ld_p2(msg_p + w[1 + j]);
+    suf[d - 1] = P2{1.0, 1.0};
 #pragma unroll
     for (int j = d - 2; j >= 0; --j) suf[j] = (j == d - 2) ? x[j + 1] : suf[j + 1] * x[j + 1];
-    double pre = lc;                           // L_ch * prod_{k < j} x_k
-    double lam[CAP];
+    P2 pre = lc;                                // L_ch * prod_{k < j} x_k
 #pragma unroll
     for (int j = 0; j < d; ++j) {
         lam[j] = (j == d - 1) ? pre : pre * suf[j];
-        if (j < d - 1) pre *= x[j];
+        if (j < d - 1) pre = pre * x[j];
     }
-    const double tot = lam[d - 1] * x[d - 1];  // posterior likelihood ratio
-    const bool one = tot <= 1.0;               // estimate <= 0 -> bit 1 (bp.h:193)
-    const int hard = one ? (int) 0x80000000 : 0;
+    const P2 tot = lam[d - 1] * x[d - 1];       // posterior likelihood ratios
+    const bool one_a = tot.a <= 1.0, one_b = tot.b <= 1.0;   // estimate <= 0 -> bit 1 (bp.h:193)
+    const int sa = one_a ? (int) 0x80000000 : 0, sb = one_b ? (int) 0x80000000 : 0;
 #pragma unroll
-    for (int j = 0; j < d; ++j) {
-        const int hi = min(max(__double2hiint(lam[j]), clamp_lo), clamp_hi) | hard;
-        st_f64(msg_f + w[1 + j], __hiloint2double(hi, __double2loint(lam[j])));
-    }
-    dec_f[w[0] / 8] = (uint8_t) one;
-    if (SOFT) st_f64(post_f + w[0], tot);
+    for (int j = 0; j < d; ++j)
+        st_p2(msg_p + w[1 + j], P2{clamp_sign(lam[j].a, clamp_lo, clamp_hi, sa), clamp_sign(lam[j].b, clamp_lo, clamp_hi, sb)});
+    *reinterpret_cast<uint16_t *>(dec_p + (w[0] >> 3)) = (uint16_t) ((one_a ? 1 : 0) | (one_b ? 0x100 : 0));
+    if (SOFT) st_p2(post_p + w[0], tot);
 }
 
-// the initial send (bp.h:184): all C->V messages are zero (CNode::init, bp.h:42-45), i.e. x = 1
-template <int D, int FB, bool SOFT>
-__device__ __forceinline__ void lr_var_first(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
-                                             const LrRec<D> &r, int d_runtime, int clamp_lo, int clamp_hi) {
-    const int d = D > 0 ? D : d_runtime;
-    const uint32_t *w = r.w;
-    const double lc = ld_f64(lch_f + w[0]);
-    const double l = clamp_hi_word(lc, clamp_lo, clamp_hi);
-    const int hard = lc <= 1.0 ? (int) 0x80000000 : 0;
-    const double m = __hiloint2double(__double2hiint(l) | hard, __double2loint(l));
-#pragma unroll
-    for (int j = 0; j < d; ++j) st_f64(msg_f + w[1 + j], m);
-    dec_f[w[0] / 8] = (uint8_t) (lc <= 1.0);
-    if (SOFT) st_f64(post_f + w[0], lc);
-}
-
-// one step of the variable pass: 32/F consecutive ranks of degree D, one per lane group
-template <int D, int F, bool SOFT>
-__device__ __forceinline__ void lr_var_step(char *msg_f, const char *lch_f, char *post_f, uint8_t *dec_f,
-                                            const uint32_t *rec, int degree, int node_lane, bool fresh,
-                                            int clamp_lo, int clamp_hi) {
-    const int stride = D > 0 ? ((D + 1 + 3) / 4) * 4 : ((degree + 1 + 3) / 4) * 4;
-    LrRec<D> r;
-    r.load(rec + node_lane * stride, degree);
-    if (fresh) lr_var_first<D, F * 8, SOFT>(msg_f, lch_f, post_f, dec_f, r, degree, clamp_lo, clamp_hi);
-    else lr_var_update<D, F * 8, SOFT>(msg_f, lch_f, post_f, dec_f, r, degree, clamp_lo, clamp_hi);
-}
-
-// ---- check node of degree D: CNode::message (bp.h:49-57); returns the parity of the decisions
+// ---- check node of degree D, two frames: CNode::message (bp.h:49-57); returns the parities of the decisions
+// (bit 0 / bit 1 = first / second frame of the pair).  edge = first message of the node, lane's frame pair.
 template <int D, int FB>
 __device__ __forceinline__ int lr_chk_update(char *edge, int d_runtime, int clamp_hi) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
-    double a[CAP], se[CAP], so[CAP];
-    int par = 0;
+    P2 a[CAP], se[CAP], so[CAP];
+    int par_a = 0, par_b = 0;
 #pragma unroll
     for (int j = 0; j < d; ++j) {
-        const double m = ld_f64(edge + j * FB);
-        const int hi = __double2hiint(m);
-        par ^= hi;
-        a[j] = __hiloint2double(hi & 0x7fffffff, __double2loint(m));
+        const P2 m = ld_p2(edge + j * FB);
+        par_a ^= __double2hiint(m.a);
+        par_b ^= __double2hiint(m.b);
+        a[j] = P2{fabs(m.a), fabs(m.b)};
     }
+    const int par = (int) ((unsigned) par_a >> 31) | (int) (((unsigned) par_b >> 31) << 1);
     if (d == 1) {                               // no other variable: phi(0) = +inf in the reference; here the cap
-        st_f64(edge, __hiloint2double(clamp_hi, 0));
-        return (unsigned) par >> 31;
+        const double cap = __hiloint2double(clamp_hi, 0);
+        st_p2(edge, P2{cap, cap});
+        return par;
     }
+    const P2 one{1.0, 1.0};
     // suffix pairs S_j = (Pe, Po) over the inputs i > j
-    se[d - 1] = 1.0;
-    so[d - 1] = 0.0;
+    se[d - 1] = one;
+    so[d - 1] = P2{0.0, 0.0};
 #pragma unroll
     for (int j = d - 2; j >= 0; --j) {
-        if (j == d - 2) { se[j] = a[j + 1]; so[j] = 1.0; }
-        else { se[j] = __fma_rn(se[j + 1], a[j + 1], so[j + 1]); so[j] = __fma_rn(so[j + 1], a[j + 1], se[j + 1]); }
+        if (j == d - 2) { se[j] = a[j + 1]; so[j] = one; }
+        else { se[j] = fma2(se[j + 1], a[j + 1], so[j + 1]); so[j] = fma2(so[j + 1], a[j + 1], se[j + 1]); }
     }
-    double pe = 1.0, po = 0.0;                  // prefix pair over the inputs i < j
+    P2 pe = one, po{0.0, 0.0};                  // prefix pair over the inputs i < j
 #pragma unroll
     for (int j = 0; j < d; ++j) {
-        double ev, od;
+        P2 ev, od;
         if (j == 0) { ev = se[0]; od = so[0]; }
         else if (j == d - 1) { ev = pe; od = po; }
-        else if (j == 1) { ev = __fma_rn(pe, se[j], so[j]); od = __fma_rn(pe, so[j], se[j]); }   // (pe, po) = (a0, 1)
-        else { ev = __fma_rn(pe, se[j], po * so[j]); od = __fma_rn(pe, so[j], po * se[j]); }
-        st_f64(edge + j * FB, div_pos(ev, od));
-        if (j == 0) { pe = a[0]; po = 1.0; }
-        else if (j < d - 1) { const double ne = __fma_rn(pe, a[j], po); po = __fma_rn(po, a[j], pe); pe = ne; }
+        else if (j == 1) { ev = fma2(pe, se[j], so[j]); od = fma2(pe, so[j], se[j]); }   // (pe, po) = (a0, 1)
+        else { ev = fma2(pe, se[j], po * so[j]); od = fma2(pe, so[j], po * se[j]); }
+        st_p2(edge + j * FB, div2(ev, od));
+        if (j == 0) { pe = a[0]; po = one; }
+        else if (j < d - 1) { const P2 ne = fma2(pe, a[j], po); po = fma2(po, a[j], pe); pe = ne; }
     }
-    return (unsigned) par >> 31;
+    return par;
 }
 
 template <int F, int MAXT>
@@ -212,20 +204,25 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     const KernelIO &io = p.io;
     const int n = io.n;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int warp = tid >> 5, nwarps = nt >> 5, lane = tid & 31;
-    constexpr int FB = F * 8;
-    const int f_lane = lane % F, node_lane = lane / F;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int FB = F * 8;                   // bytes between consecutive elements
+    constexpr int LPN = F / 2;                  // lanes per node
+    const int pair = lane % LPN, node_lane = lane / LPN;
 
     char *msg = reinterpret_cast<char *>(smem);                          // E x F doubles
     char *lch = msg + (size_t) p.E * FB;                                 // n x F doubles
     char *post = lch + (size_t) n * FB;                                  // n x F doubles (soft output only)
-    uint8_t *dec = reinterpret_cast<uint8_t *>(post + (p.soft ? (size_t) n * FB : 0));   // n x F bytes
+    uint32_t *rec = reinterpret_cast<uint32_t *>(post + (p.soft ? (size_t) n * FB : 0));   // variable records
+    uint32_t *steps = rec + p.rec_words;                                 // this CTA's copy of the step lists
+    uint8_t *dec = reinterpret_cast<uint8_t *>(steps + (size_t) (nt >> 5) * p.steps_per_warp);   // n x F bytes
     uint8_t *cw = dec + (size_t) n * F;                                  // F x n bytes (experiment mode)
     LrShared<F> *L = reinterpret_cast<LrShared<F> *>(
         (reinterpret_cast<uintptr_t>(cw + (io.experiment ? (size_t) n * F : 0)) + 15) & ~(uintptr_t) 15);
     SlotBlock<F> *S = &L->S;
 
     slots_init(S);
+    for (int i = tid; i < p.rec_words; i += nt) rec[i] = p.rec_v[i];
+    for (int i = tid; i < (nt >> 5) * p.steps_per_warp; i += nt) steps[i] = p.steps[i];
     if (tid == 0) {
         L->ctl[0] = LrCtl{0u, 0u, 0u, 0u};
         L->ctl[1] = LrCtl{0u, 0u, 0u, 0u};
@@ -236,44 +233,39 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     }
     __syncthreads();
 
-    char *msg_f = msg + f_lane * 8;
-    const char *lch_f = lch + f_lane * 8;
-    char *post_f = post + f_lane * 8;
+    char *msg_p = msg + pair * 16;
+    const char *lch_p = lch + pair * 16;
+    char *post_p = post + pair * 16;
+    uint8_t *dec_p = dec + pair * 2;
     const bool soft = p.soft != 0;
-    // this warp's steps of the two passes, heaviest degree first, terminated by degree 0
-    const BpLrRun *my_steps_v = p.runs_v + (size_t) warp * p.max_runs_v;
-    const BpLrRun *my_steps_c = p.runs_c + (size_t) warp * p.max_runs_c;
-    uint8_t *dec_f = dec + f_lane;
+    const uint32_t *my_steps_v = steps + (size_t) warp * p.steps_per_warp;
+    const uint32_t *my_steps_c = my_steps_v + p.steps_c_off;
+    const unsigned pair_bits = 3u << (2 * pair);
 
     for (unsigned trip = 0;; ++trip) {
         LrCtl *ctl = &L->ctl[trip & 1];
         // ---- check pass (also the syndrome of the previous variable pass)
         const unsigned active = ctl->active;
         if (active) {
-            int bad = 0;
-            if ((active >> f_lane) & 1u) {
-                const BpLrRun *q = my_steps_c;
-                BpLrRun e = *q;
-                while (e.degree > 8) {
-                    const BpLrRun nx = *++q;
-                    if (node_lane < e.nodes)
-                        bad |= lr_chk_update<0, FB>(msg_f + e.first + node_lane * e.degree * FB, e.degree, p.clamp_hi);
-                    e = nx;
-                }
-#define LDPC_CHK_STEPS(D)                                                                                   \
-    while (e.degree == D) {                                                                                 \
-        const BpLrRun nx = *++q;                                                                            \
-        if (node_lane < e.nodes) bad |= lr_chk_update<D, FB>(msg_f + e.first + node_lane * D * FB, D, p.clamp_hi); \
+            unsigned bad = 0;
+            if (active & pair_bits) {
+                const uint32_t *q = my_steps_c;
+                uint32_t e = *q;
+#define LDPC_CHK_STEPS(D, COND)                                                                             \
+    while (COND) {                                                                                          \
+        const uint32_t nx = *++q;                                                                           \
+        const int deg = (int) (e >> 23);                                                                    \
+        if (node_lane <= (int) ((e >> 18) & 31u))                                                           \
+            bad |= (unsigned) lr_chk_update<D, FB>(msg_p + (e & 0x3ffffu) + node_lane * deg * FB, deg, p.clamp_hi); \
         e = nx;                                                                                             \
     }
-                LDPC_CHK_STEPS(8) LDPC_CHK_STEPS(7) LDPC_CHK_STEPS(6) LDPC_CHK_STEPS(5)
-                LDPC_CHK_STEPS(4) LDPC_CHK_STEPS(3) LDPC_CHK_STEPS(2) LDPC_CHK_STEPS(1)
+                LDPC_CHK_STEPS(0, (e >> 23) > 8)
+                LDPC_CHK_STEPS(8, (e >> 23) == 8) LDPC_CHK_STEPS(7, (e >> 23) == 7) LDPC_CHK_STEPS(6, (e >> 23) == 6)
+                LDPC_CHK_STEPS(5, (e >> 23) == 5) LDPC_CHK_STEPS(4, (e >> 23) == 4) LDPC_CHK_STEPS(3, (e >> 23) == 3)
+                LDPC_CHK_STEPS(2, (e >> 23) == 2) LDPC_CHK_STEPS(1, (e >> 23) == 1)
 #undef LDPC_CHK_STEPS
             }
-            unsigned b = __ballot_sync(0xffffffffu, bad);
-#pragma unroll
-            for (int s = F; s < 32; s <<= 1) b |= b >> s;      // fold the node lanes: bit f = slot f
-            b &= (F == 32) ? 0xffffffffu : ((1u << F) - 1u);
+            const unsigned b = __reduce_or_sync(0xffffffffu, bad << (2 * pair));
             if (lane == 0 && b) atomicOr(&ctl->bad, b);
         }
         __syncthreads();
@@ -332,6 +324,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
             if (S->alive == 0) break;
             const unsigned fresh = L->fresh;
             if (fresh) {
+                // all C->V messages of a new frame are zero (CNode::init, bp.h:42-45): x = 1, which makes its first
+                // variable pass the reference's initial send (bp.h:184)
+                for (int i = tid; i < p.E * F; i += nt)
+                    if ((fresh >> (i % F)) & 1u) st_f64(msg + (size_t) i * 8, 1.0);
                 // L_ch = exp(llr), llr clamped to +-llr_cap; variables without edges keep decision / posterior of the channel
                 slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int f, double l) {
                     const double lc = exp_signed(fmin(fmax(l, -p.llr_cap), p.llr_cap));
@@ -343,9 +339,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         }
 
         // ---- variable pass
-        const unsigned live = L->live, fresh = L->fresh;
+        const unsigned live = L->live;
         if (warp == 0) {
             // control words of the next trip
+            const unsigned fresh = L->fresh;
             int it = 0;
             if (lane < F && ((live >> lane) & 1u)) {
                 it = ((fresh >> lane) & 1u) ? 0 : S->iter[lane] + 1;
@@ -354,45 +351,42 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
             }
             const unsigned elig = __ballot_sync(0xffffffffu, it >= 1) & live;
             const unsigned atmax = __ballot_sync(0xffffffffu, it >= p.max_iter) & live;
-            if (lane == 0) L->ctl[(trip + 1) & 1] = LrCtl{live, elig, atmax, 0u};
+            if (lane == 0) {
+                L->ctl[(trip + 1) & 1] = LrCtl{live, elig, atmax, 0u};
+                L->fresh = 0u;
+            }
         }
-        if ((live >> f_lane) & 1u) {
-            const bool is_fresh = (fresh >> f_lane) & 1u;
-            const BpLrRun *q = my_steps_v;
-            BpLrRun e = *q;
-#define LDPC_VAR_STEP(D)                                                                                          \
-    do {                                                                                                          \
-        const BpLrRun nx = *++q;                                                                                  \
-        if (node_lane < e.nodes) {                                                                                \
-            if (soft) lr_var_step<D, F, true>(msg_f, lch_f, post_f, dec_f, p.rec_v + e.first, e.degree, node_lane, \
-                                              is_fresh, p.clamp_lo, p.clamp_hi);                                  \
-            else lr_var_step<D, F, false>(msg_f, lch_f, post_f, dec_f, p.rec_v + e.first, e.degree, node_lane,    \
-                                          is_fresh, p.clamp_lo, p.clamp_hi);                                      \
+        if (live & pair_bits) {
+            const uint32_t *q = my_steps_v;
+            uint32_t e = *q;
+#define LDPC_VAR_STEPS(D, COND)                                                                                   \
+    while (COND) {                                                                                                \
+        const uint32_t nx = *++q;                                                                                 \
+        const int deg = (int) (e >> 23);                                                                          \
+        if (node_lane <= (int) ((e >> 18) & 31u)) {                                                               \
+            const int words = ((deg + 1 + 3) / 4) * 4;                                                            \
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(rec) + (e & 0x3ffffu)) + node_lane * words; \
+            if (soft) lr_var_update<D, true>(msg_p, lch_p, post_p, dec_p, r, deg, p.clamp_lo, p.clamp_hi);        \
+            else lr_var_update<D, false>(msg_p, lch_p, post_p, dec_p, r, deg, p.clamp_lo, p.clamp_hi);            \
         }                                                                                                         \
         e = nx;                                                                                                   \
-    } while (0)
-            while (e.degree > 8) LDPC_VAR_STEP(0);
-            while (e.degree == 8) LDPC_VAR_STEP(8);
-            while (e.degree == 7) LDPC_VAR_STEP(7);
-            while (e.degree == 6) LDPC_VAR_STEP(6);
-            while (e.degree == 5) LDPC_VAR_STEP(5);
-            while (e.degree == 4) LDPC_VAR_STEP(4);
-            while (e.degree == 3) LDPC_VAR_STEP(3);
-            while (e.degree == 2) LDPC_VAR_STEP(2);
-            while (e.degree == 1) LDPC_VAR_STEP(1);
-#undef LDPC_VAR_STEP
+    }
+            LDPC_VAR_STEPS(0, (e >> 23) > 8)
+            LDPC_VAR_STEPS(8, (e >> 23) == 8) LDPC_VAR_STEPS(7, (e >> 23) == 7) LDPC_VAR_STEPS(6, (e >> 23) == 6)
+            LDPC_VAR_STEPS(5, (e >> 23) == 5) LDPC_VAR_STEPS(4, (e >> 23) == 4) LDPC_VAR_STEPS(3, (e >> 23) == 3)
+            LDPC_VAR_STEPS(2, (e >> 23) == 2) LDPC_VAR_STEPS(1, (e >> 23) == 1)
+#undef LDPC_VAR_STEPS
         }
         __syncthreads();
-        if (tid == 0 && fresh) L->fresh = 0u;      // read again only after the next barrier
     }
     slots_flush(io, S);
 }
 
 // ---------------------------------------------------------------- host side
 
-static size_t lr_smem_bytes(const ldpc_code *c, int F, bool soft, bool experiment) {
+static size_t lr_smem_bytes(const ldpc_code *c, int F, bool soft, bool experiment, int rec_words, int step_words) {
     return (size_t) F * 8 * ((size_t) c->E + (size_t) c->n * (soft ? 2 : 1)) + (size_t) F * c->n * (experiment ? 2 : 1) +
-           16 + sizeof(SlotBlock<32>) + 256;
+           (size_t) 4 * (rec_words + step_words) + 16 + sizeof(SlotBlock<32>) + 256;
 }
 
 // message cap C1: products of (dv - 1) messages times L_ch, and of (dc - 1) messages, must stay inside the double range
@@ -405,28 +399,27 @@ double bp_lr_cap(const ldpc_code *c, double *llr_cap_out) {
     return c1;
 }
 
-// Deals the steps (32/F consecutive node ranks of one degree class = one node per lane group) to the warps
+static int rec_words_of(const ldpc_code *c) {
+    int words = 0;
+    for (const BpClass &cl : c->var_classes) words += cl.count * (((cl.degree + 1 + 3) / 4) * 4);
+    return words;
+}
+
+// Deals the steps (64/F consecutive node ranks of one degree class = one node per lane group) to the warps
 // round-robin, heaviest classes first, so the warps of a pass finish together.  Per warp: its steps in that
-// order, terminated by a degree-0 entry.
+// order, terminated by a 0 word.
 template <typename FirstOf>
-static std::vector<BpLrRun> make_runs(const std::vector<BpClass> &classes, int F, int nwarps, int *max_runs,
-                                      FirstOf first_of) {
-    const int G = 32 / F;
+static std::vector<std::vector<uint32_t>> deal_steps(const std::vector<BpClass> &classes, int F, int nwarps, FirstOf first_of) {
+    const int G = 64 / F;
     std::vector<int> order(classes.size());
     for (size_t k = 0; k < classes.size(); ++k) order[k] = (int) k;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return classes[a].degree > classes[b].degree; });
-    std::vector<std::vector<BpLrRun>> per_warp(nwarps);
+    std::vector<std::vector<uint32_t>> per_warp(nwarps);
     int s_global = 0;
     for (int k : order)
         for (int n0 = 0; n0 < classes[k].count; n0 += G, ++s_global)
-            per_warp[s_global % nwarps].push_back(BpLrRun{(uint16_t) classes[k].degree,
-                                                          (uint16_t) std::min(G, classes[k].count - n0), first_of(k, n0)});
-    size_t mr = 1;
-    for (auto &rw : per_warp) mr = std::max(mr, rw.size() + 1);
-    std::vector<BpLrRun> flat((size_t) nwarps * mr, BpLrRun{0, 0, 0});
-    for (int w = 0; w < nwarps; ++w) std::copy(per_warp[w].begin(), per_warp[w].end(), flat.begin() + (size_t) w * mr);
-    *max_runs = (int) mr;
-    return flat;
+            per_warp[s_global % nwarps].push_back(lr_step_word(first_of(k, n0), std::min(G, classes[k].count - n0), classes[k].degree));
+    return per_warp;
 }
 
 template <typename T>
@@ -456,7 +449,7 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
         // variable records in rank order (classes of equal degree are adjacent, code.cu)
         std::vector<uint32_t> rec, first_v;
         for (const BpClass &cl : c->var_classes) {
-            first_v.push_back((uint32_t) rec.size());
+            first_v.push_back((uint32_t) rec.size() * 4);     // byte offset
             const int stride = ((cl.degree + 1 + 3) / 4) * 4;
             for (int k = 0; k < cl.count; ++k) {
                 const int v = c->var_order[cl.first + k];
@@ -467,16 +460,27 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                     rec[base + 1 + j] = (uint32_t) slot_of_edge[c->csc_edge[c->col_ptr[v] + j]] * F * 8;
             }
         }
-        std::vector<BpLrRun> rv = make_runs(c->var_classes, F, nwarps, &s.max_runs_v, [&](int cls, int node0) {
-            return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 4);
+        if (rec.size() * 4 >= (1u << 18) || (size_t) c->E * F * 8 >= (1u << 18))
+            return fail(LDPC_E_UNSUPPORTED, "code too large for the 18-bit step offsets of the BP kernel");
+        auto sv = deal_steps(c->var_classes, F, nwarps, [&](int cls, int node0) {
+            return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 16);
         });
-        std::vector<BpLrRun> rc = make_runs(c->chk_classes, F, nwarps, &s.max_runs_c, [&](int cls, int node0) {
+        auto sc = deal_steps(c->chk_classes, F, nwarps, [&](int cls, int node0) {
             return (uint32_t) (class_slot0[cls] + node0 * c->chk_classes[cls].degree) * F * 8;
         });
+        size_t mv = 1, mc = 1;
+        for (int w = 0; w < nwarps; ++w) { mv = std::max(mv, sv[w].size() + 1); mc = std::max(mc, sc[w].size() + 1); }
+        std::vector<uint32_t> steps((size_t) nwarps * (mv + mc), 0u);
+        for (int w = 0; w < nwarps; ++w) {
+            std::copy(sv[w].begin(), sv[w].end(), steps.begin() + (size_t) w * (mv + mc));
+            std::copy(sc[w].begin(), sc[w].end(), steps.begin() + (size_t) w * (mv + mc) + mv);
+        }
+        s.rec_words = (int) rec.size();
+        s.steps_per_warp = (int) (mv + mc);
+        s.steps_c_off = (int) mv;
         int st;
         if ((st = upload_vec(&s.rec_v, rec))) return st;
-        if ((st = upload_vec(&s.runs_v, rv))) return st;
-        if ((st = upload_vec(&s.runs_c, rc))) return st;
+        if ((st = upload_vec(&s.steps, steps))) return st;
         it = c->bp_lr_sched.emplace(std::make_pair(F, nwarps), s).first;
     }
     *out = it->second;
@@ -484,12 +488,14 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
 }
 
 template <int F, int MAXT>
-static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
+static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, int64_t frames, cudaStream_t stream) {
     BpLrSchedule s;
     int st = get_lr_schedule(c, F, threads / 32, &s);
     if (st) return st;
-    p.rec_v = s.rec_v; p.runs_v = s.runs_v; p.runs_c = s.runs_c;
-    p.max_runs_v = s.max_runs_v; p.max_runs_c = s.max_runs_c;
+    p.rec_v = s.rec_v; p.steps = s.steps; p.rec_words = s.rec_words;
+    p.steps_per_warp = s.steps_per_warp; p.steps_c_off = s.steps_c_off;
+    const size_t smem = lr_smem_bytes(c, F, p.soft != 0, p.io.experiment != 0, s.rec_words, s.steps_per_warp * (threads / 32));
+    if (smem > 227 * 1024) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
     auto kernel = bp_lr_kernel<F, MAXT>;
     LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
@@ -505,12 +511,13 @@ static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, size_t s
     return LDPC_OK;
 }
 
-// register budget by CTA size: 128 / 85 / 64 registers per thread
+// register budget by CTA size: 128 / 85 registers per thread
 template <int F>
-static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, size_t smem, int64_t frames, cudaStream_t stream) {
-    if (threads <= 512) return launch_lr_ft<F, 512>(p, c, threads, smem, frames, stream);
-    if (threads <= 768) return launch_lr_ft<F, 768>(p, c, threads, smem, frames, stream);
-    return launch_lr_ft<F, 1024>(p, c, threads, smem, frames, stream);
+static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, int64_t frames, cudaStream_t stream) {
+    int maxt = threads <= 512 ? 512 : 768;
+    if (const char *force = getenv("LDPC_BP_MAXT")) maxt = atoi(force) > 512 ? 768 : 512;
+    if (maxt == 512 && threads <= 512) return launch_lr_ft<F, 512>(p, c, threads, frames, stream);
+    return launch_lr_ft<F, 768>(p, c, threads, frames, stream);
 }
 
 int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
@@ -536,27 +543,28 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
         p.clamp_hi = (int) (bhi >> 32);
     }
     const bool exp_mode = fio.experiment != 0;
+    const int rec_words = rec_words_of(c);
     int F = 16;
     if (const char *force = getenv("LDPC_BP_F")) {
         const int v = atoi(force);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) F = v;
+        if (v == 2 || v == 4 || v == 8 || v == 16) F = v;
     } else {
-        while (F > 1 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
+        while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
     }
-    while (F > 1 && lr_smem_bytes(c, F, p.soft, exp_mode) > 227 * 1024) F >>= 1;
-    const size_t smem = lr_smem_bytes(c, F, p.soft, exp_mode);
-    if (smem > 227 * 1024) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
-    int threads = (long long) c->n * F >= 2048 ? 512 : 256;
+    while (F > 2 && lr_smem_bytes(c, F, p.soft, exp_mode, rec_words, 64 * 24) > 227 * 1024) F >>= 1;
+    // warps per CTA: about three steps per warp and pass (measured on B200: throughput is flat from 16 to 24 warps,
+    // profiles/r01_bp_lr_sweep.txt; more warps hide the barrier and shared-memory latencies of the short passes)
+    const int lanes = std::max(c->n, c->m) * (F / 2);
+    int threads = std::min(768, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
-        if (v >= 32 && v <= 1024) threads = v;
+        if (v >= 32 && v <= 768) threads = v;
     }
     switch (F) {
-        case 16: return launch_lr_f<16>(p, c, threads, smem, frames, stream);
-        case 8: return launch_lr_f<8>(p, c, threads, smem, frames, stream);
-        case 4: return launch_lr_f<4>(p, c, threads, smem, frames, stream);
-        case 2: return launch_lr_f<2>(p, c, threads, smem, frames, stream);
-        default: return launch_lr_f<1>(p, c, threads, smem, frames, stream);
+        case 16: return launch_lr_f<16>(p, c, threads, frames, stream);
+        case 8: return launch_lr_f<8>(p, c, threads, frames, stream);
+        case 4: return launch_lr_f<4>(p, c, threads, frames, stream);
+        default: return launch_lr_f<2>(p, c, threads, frames, stream);
     }
 }
 

@@ -167,7 +167,7 @@ void ldpc_code_destroy(ldpc_code_t *c) {
     cudaFree(c->d.gen_cols);
     for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
     for (auto &kv : c->bp_lr_sched) {
-        cudaFree(kv.second.rec_v); cudaFree(kv.second.runs_v); cudaFree(kv.second.runs_c);
+        cudaFree(kv.second.rec_v); cudaFree(kv.second.steps);
     }
     delete c;
 }

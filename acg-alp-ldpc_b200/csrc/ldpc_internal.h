@@ -47,16 +47,10 @@ struct BpSchedule {   // device arrays, rounds x warps jobs each (log-domain ker
     int rounds_v = 0, rounds_c = 0;
 };
 // likelihood-ratio BP kernel (bp_lr_kernel.cu): tables depend on the frames per CTA (byte offsets are pre-scaled)
-struct alignas(8) BpLrRun {   // consecutive node ranks of one degree, processed by one warp (32/F nodes per step)
-    uint16_t degree;          // 0 = end of the warp's list
-    uint16_t nodes;
-    uint32_t first;           // variable pass: word offset of the first node record; check pass: byte offset of
-                              // the first message of the first node
-};
 struct BpLrSchedule {
-    uint32_t *rec_v = nullptr;
-    BpLrRun *runs_v = nullptr, *runs_c = nullptr;
-    int max_runs_v = 0, max_runs_c = 0;
+    uint32_t *rec_v = nullptr;    // variable node records
+    uint32_t *steps = nullptr;    // per warp: variable-pass steps, check-pass steps (bp_lr_kernel.cu: lr_step_word)
+    int rec_words = 0, steps_per_warp = 0, steps_c_off = 0;
 };
 
 // QP-ADMM works per BLOCK: one three-variable check of the chain decomposition

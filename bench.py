@@ -35,7 +35,10 @@ SEED = 239239239
 BP_SNR, BP_ITERS = -5.0, 100
 ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
 # algorithmic fp64 instructions per unit of work (DESIGN.md "rooflines"):
-BP_FP64_PER_EDGE_ITER = 48.0          # exp 15 + log-ratio 19 + leave-one-out products 9 + sums 3 + sign/abs 2
+# BP in the likelihood-ratio domain: per edge and iteration
+BP_FP64_PER_EDGE_ITER = 12.0          # check: 5.3 Pe/Po recurrences + 5 division; variable: 2.7 products + decision
+BP_SMEM_BYTES_PER_EDGE_ITER = 32.0    # each message is read and written once per pass (8 B), two passes
+BP_SMEM_BYTES_PER_VAR_ITER = 8.0      # channel likelihood ratio
 ADMM_FP64_PER_BLOCK_ITER = 42.0       # 12 gather adds + 9 residual + 17 row updates (4 t, 4 d, 1 zb, 8 fma) + 4 v ops
 
 
@@ -283,16 +286,28 @@ def run_gpu(args):
         achieved = fps_gpu * n_iter * units * per_unit / 1e9            # G fp64 instr/s on one GPU
         bytes_per_frame = n * 8 + n + 1 + 4
         k = info["n"] - info["m"]
+        fp64 = {"achieved": achieved, "peak": fp64_peak, "unit": "Gop/s (fp64 instr)", "frac": achieved / fp64_peak,
+                "peak_source": "ldpc_measure_fp64_peak on this GPU (8 independent DFMA chains/thread)",
+                "work_per_launch": "%d frames x %d iters x %d %s x %.0f fp64 instr" % (
+                    frames, n_iter, units, "edges" if algo == "bp" else "blocks", per_unit)}
+        hbm = {"achieved": fps_gpu * bytes_per_frame / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": fps_gpu * bytes_per_frame / 1e9 / hbm_peak, "peak_kind": peak_kind}
+        if algo == "bp":
+            # messages never leave the SM: the bounding resource of the likelihood-ratio kernel is shared-memory
+            # bandwidth (algorithmic bytes below), then the FP64 pipe; HBM carries 2.5 KB per frame
+            smem_bytes = info["edges"] * BP_SMEM_BYTES_PER_EDGE_ITER + info["n"] * BP_SMEM_BYTES_PER_VAR_ITER
+            got = fps_gpu * n_iter * smem_bytes / 1e9
+            roof = {"bound": "smem", "achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
+                    "traffic": None, "bytes_per_frame_iter": smem_bytes,
+                    "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)",
+                    "work_per_launch": "%d frames x %d iters x %.0f B of shared-memory traffic" % (frames, n_iter, smem_bytes),
+                    "fp64": fp64, "hbm": hbm}
+        else:
+            roof = dict(fp64, bound="fp64", traffic=None, hbm=hbm)
         res = {
             "value": value, "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
             "info_gbit_per_s": value * k / 1e9,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "Gop/s (fp64 instr)",
-                         "frac": achieved / fp64_peak, "traffic": None,
-                         "peak_source": "ldpc_measure_fp64_peak on this GPU (8 independent DFMA chains/thread)",
-                         "work_per_launch": "%d frames x %d iters x %d %s x %.0f fp64 instr" % (
-                             frames, n_iter, units, "edges" if algo == "bp" else "blocks", per_unit),
-                         "hbm": {"achieved": fps_gpu * bytes_per_frame / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": fps_gpu * bytes_per_frame / 1e9 / hbm_peak, "peak_kind": peak_kind}},
+            "roofline": roof,
             "e2e": {"value": world * e2e_frames * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": e2e_frames * n * 8, "d2h_bytes_per_step": e2e_frames * (n + 5)},
             "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),

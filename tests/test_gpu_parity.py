@@ -104,10 +104,15 @@ def test_bp_matches_fp80_oracle(codes, oracle, name, snrs, frames):
     assert mism == 0, "%d of %d frames differ" % (mism, total)
 
 
-@pytest.mark.parametrize("slots", ["2", "4"])
+@pytest.mark.parametrize("slots", ["2", "4", "8", "16", "log"])
 def test_bp_multi_slot_kernels(codes, oracle, slots, monkeypatch):
-    """F frames per CTA with slot refill: same per-frame results as the oracle, whatever the schedule"""
-    monkeypatch.setenv("LDPC_BP_F", slots)
+    """F frames per CTA with slot refill: same per-frame results as the oracle, whatever the schedule
+    ("log" = the log-domain kernel that serves codes with very large node degrees)"""
+    if slots == "log":
+        monkeypatch.setenv("LDPC_BP_KERNEL", "log")
+        monkeypatch.setenv("LDPC_BP_F", "4")
+    else:
+        monkeypatch.setenv("LDPC_BP_F", slots)
     for name, frames, snr in (("optimalH", 301, -3.0), ("H05", 150, -2.0), ("reg_3_6_1008", 21, -1.0)):
         H, code, csr = codes[name]
         m, n = H.shape
