@@ -165,6 +165,7 @@ void ldpc_code_destroy(ldpc_code_t *c) {
     cudaFree(c->d.col_ptr); cudaFree(c->d.row_ptr); cudaFree(c->d.col_idx);
     cudaFree(c->d.blocks); cudaFree(c->d.admm_var); cudaFree(c->d.admm_inc); cudaFree(c->d.admm_var_id); cudaFree(c->d.admm_var_rank);
     cudaFree(c->d.gen_cols);
+    free_chk_tables(c);
     for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
     for (auto &kv : c->bp_lr_sched) {
         cudaFree(kv.second.rec_v); cudaFree(kv.second.steps);

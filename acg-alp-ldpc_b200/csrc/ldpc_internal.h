@@ -72,6 +72,16 @@ struct AdmmVarRec {   // indexed by variable rank
     uint16_t pad1;
 };
 
+// tables of the check-centric QP-ADMM kernel (qpadmm_chk_kernel.cu), built on first use
+struct AdmmChkTables {
+    bool built = false, supported = false;
+    uint32_t *chk_tab = nullptr, *var_words = nullptr;
+    uint4 *var_inc = nullptr;
+    uint16_t *var_rank = nullptr, *var_e = nullptr;
+    uint32_t plane_base[6] = {0, 0, 0, 0, 0, 0};
+    int n_chunks = 0, n_inc = 0, tab_stride = 0, max_nb = 0, e_min = 0;
+};
+
 struct DeviceTables {
     // BP
     uint16_t *chk_rs = nullptr;    // check rank -> CSR position of its first edge
@@ -109,6 +119,7 @@ struct ldpc_code {
     mutable std::mutex sched_mu;
     mutable std::map<std::pair<int, int>, ldpc::BpSchedule> bp_sched;
     mutable std::map<std::pair<int, int>, ldpc::BpLrSchedule> bp_lr_sched;
+    mutable ldpc::AdmmChkTables admm_chk;
 };
 
 namespace ldpc {
@@ -142,6 +153,12 @@ int launch_bp_log(const ldpc_code *code, const FrameIO &io, int64_t frames, doub
 double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
+// the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 3..8) and block-per-lane (any code)
+int launch_qpadmm_chk(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
+                      double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
+int launch_qpadmm_blk(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
+                      double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
+void free_chk_tables(ldpc_code *code);
 int launch_channel(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames, double sigma,
                    const uint8_t *d_codewords, double *d_y, cudaStream_t stream);
 int launch_generator_codewords(const ldpc_code *code, uint64_t seed, uint64_t frame_begin, int64_t frames,

@@ -1,0 +1,524 @@
+// QP-ADMM decoding, check-centric kernel (sm_100a) -- DecodeQPADMM, algo/qp_admm.h:104-178, for codes
+// whose checks all have degree 3..8 (every code of BASELINE.json).  qpadmm_kernel.cu serves the rest.
+//
+// ConstructADMMProblem (qp_admm.h:59-92) splits a check of degree d into a chain of d - 2 three-variable
+// blocks that are linked by d - 3 auxiliary variables, and every auxiliary variable belongs to exactly two
+// consecutive blocks of ONE check.  So one lane owns one (check, frame) pair for the whole life of the
+// frame and keeps in registers
+//     yl[k][4]   the duals of its blocks (the reference's z is a function of the same number, admm_rows.cuh)
+//     aux[k]     the values of its auxiliary variables
+// and only what crosses between checks and ORIGINAL variables goes through shared memory:
+//     w01 / w23  the four row terms w = yl + mu (z - b) of every block (two 16-byte chunks per frame), written by
+//                the check lanes, gathered by the variable lanes in ascending row order (qp_admm.h:133-138)
+//     v          the variable values (two buffers, see below), written by the variable lanes, gathered by the
+//                check lanes in ascending variable order (qp_admm.h:144-151)
+//     qa, inv    q_i + alpha/2 and -1/(mu e_i - alpha)
+// Compared with the block-per-lane kernel this drops the auxiliary variables' round trip (half of all gathers),
+// all per-iteration table loads of the check phase (the lane <-> check mapping is static) and the sign-flip
+// arithmetic of the residuals and of the auxiliary updates (signs are static there).
+// Arithmetic is fp64, every operation an _rn intrinsic in the reference's order: v, the hard decisions and the
+// iteration count are bit-identical to the reference (the summation order of the stop test is a tree).
+//
+// A trip of the main loop:
+//   variable phase   v[trip & 1] of the slots that hold a frame; warp 0 meanwhile adds up the stop sums of the
+//                    previous check phase (qp_admm.h:161-163)
+//   barrier          frames whose stop test fired (or that ran out of iterations) are published from
+//                    v[(trip - 1) & 1] -- the variable phase just executed for them is discarded -- and their
+//                    slots refilled
+//   check phase      residuals, duals, row terms, the auxiliary variables of the NEXT iteration, stop-sum partials
+//   barrier
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "admm_rows.cuh"
+#include "slots.cuh"
+
+namespace ldpc {
+
+constexpr int CHK_MAX_NB = 6;     // blocks per check (degree <= 8)
+
+struct AdmmChkParams {
+    KernelIO io;
+    const uint32_t *chk_tab;      // per check rank: (NB + 3) words: degree, then the variable RANKS of its variables (ascending variable index)
+    const uint32_t *var_words;    // per variable rank: (offset of its record in uint4 units) << 4 | incidences
+    const uint4 *var_inc;         // incidence records {chunk index, flip mask w0, flip mask w1, flip mask w2}, row order
+    const uint16_t *var_rank;     // variable index -> rank
+    const uint16_t *var_e;        // per variable rank: sum of squared coefficients of its column (qp_admm.h:94-99)
+    uint32_t plane_base[CHK_MAX_NB];   // chunk index of check rank 0's k-th block
+    int n_chk, n_var, n_chunks, n_inc, tab_stride;
+    int max_iter;
+    double alpha, mu, eps_stop;
+    int chunk;                    // frames claimed from the global queue at a time
+};
+
+struct ChkCtl {
+    unsigned live;                // slots holding a frame
+    unsigned ran;                 // slots that took part in the last check phase
+    unsigned done;                // slots whose frame is finished (set by warp 0 during the variable phase)
+    unsigned fresh;
+    long long q_next, q_end;
+};
+
+template <int F>
+struct ChkShared {
+    SlotBlock<F> S;
+    ChkCtl c;
+};
+
+__device__ __forceinline__ double clip01(double x) {       // std::max(v, 0.0) then std::min(v, 1.0), qp_admm.h:140-141
+    x = (x < 0.0) ? 0.0 : x;
+    return (1.0 < x) ? 1.0 : x;
+}
+
+// One check with NBK blocks (degree NBK + 2), one frame.  va = the values of its variables in ascending index
+// order.  Writes the row terms of its blocks, updates yl / aux, returns the partial stop sum.
+template <int NBK, int NB, int F>
+__device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double (&yl)[NB][4], double (&aux)[NB],
+                                             char *w01, char *w23, const uint32_t (&plane_off)[NB], double mu,
+                                             double half_alpha, double inv_aux) {
+    constexpr int D = NBK + 2;
+    double part = 0.0, P = 0.0;
+#pragma unroll
+    for (int k = 0; k < NBK; ++k) {
+        double r0, r1, r2, r3;
+        // the block's variables in ascending index order (originals before auxiliaries) and their slots
+        if (NBK == 1) residual_rows<0, 1, 2>(va[0], va[1], va[2], 2.0, r0, r1, r2, r3);
+        else if (k == 0) residual_rows<0, 1, 2>(va[0], va[1], aux[0], 2.0, r0, r1, r2, r3);
+        else if (k == NBK - 1) residual_rows<1, 2, 0>(va[D - 2], va[D - 1], aux[k - 1], 2.0, r0, r1, r2, r3);
+        else residual_rows<1, 0, 2>(va[k + 1], aux[k - 1], aux[k], 2.0, r0, r1, r2, r3);
+        const double w0 = row_update<false>(r0, yl[k][0], part, mu, 2.0);
+        const double w1 = row_update<false>(r1, yl[k][1], part, mu, 2.0);
+        const double w2 = row_update<false>(r2, yl[k][2], part, mu, 2.0);
+        const double w3 = row_update<true>(r3, yl[k][3], part, mu, 2.0);
+        *reinterpret_cast<double2 *>(w01 + plane_off[k]) = make_double2(w0, w1);
+        *reinterpret_cast<double2 *>(w23 + plane_off[k]) = make_double2(w2, w3);
+        // the auxiliary variable between blocks k-1 and k, for the next iteration (qp_admm.h:132-142 with q = 0):
+        // rows of block k-1 (slot 2: -,-,+,+) then rows of block k (slot 0: +,-,-,+)
+        if (k > 0) {
+            double B = __dadd_rn(P, w0);
+            B = __dadd_rn(B, -w1);
+            B = __dadd_rn(B, -w2);
+            B = __dadd_rn(B, w3);
+            aux[k - 1] = clip01(__dmul_rn(B, inv_aux));
+        }
+        if (k < NBK - 1) {
+            P = __dadd_rn(half_alpha, -w0);
+            P = __dadd_rn(P, -w1);
+            P = __dadd_rn(P, w2);
+            P = __dadd_rn(P, w3);
+        }
+    }
+    return part;
+}
+
+template <int F, int NB>
+__global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const KernelIO &io = p.io;
+    const int n = io.n, n_var = p.n_var;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int warp = tid >> 5, nwarps = nt >> 5, lane = tid & 31;
+    const int f = tid % F, cr = tid / F;              // this lane's frame slot and check rank (static)
+    const int cpt = nt / F;                           // variable ranks between the steps of a lane
+    constexpr int LPF = 32 / F;                       // lanes of one frame in a warp
+
+    char *w01 = reinterpret_cast<char *>(smem);                        // n_chunks x F x 16 B
+    char *w23 = w01 + (size_t) p.n_chunks * F * 16;
+    double *v = reinterpret_cast<double *>(w23 + (size_t) p.n_chunks * F * 16);   // 2 x n_var x F
+    double *qa = v + (size_t) 2 * n_var * F;                           // n_var x F: q_i + alpha/2
+    double *inv = qa + (size_t) n_var * F;                             // n_var: -1 / (mu e_i - alpha)
+    double *red = inv + n_var;                                         // F x 32 partial stop sums
+    uint4 *inc_s = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(red + F * 32) + 15) & ~(uintptr_t) 15);   // incidence records
+    uint32_t *vw_s = reinterpret_cast<uint32_t *>(inc_s + p.n_inc);    // variable words
+    uint8_t *cw = reinterpret_cast<uint8_t *>(vw_s + n_var);           // F x n (experiment mode)
+    ChkShared<F> *L = reinterpret_cast<ChkShared<F> *>(
+        (reinterpret_cast<uintptr_t>(cw + (io.experiment ? (size_t) n * F : 0)) + 15) & ~(uintptr_t) 15);
+    SlotBlock<F> *S = &L->S;
+
+    slots_init(S);
+    // inv_coef, qp_admm.h:123-127 (A = (mu e - alpha)/2; inv = -1/(2A))
+    for (int r = tid; r < n_var; r += nt) {
+        const double A = __dmul_rn(__dadd_rn(__dmul_rn(p.mu, (double) p.var_e[r]), -p.alpha), 0.5);
+        inv[r] = __ddiv_rn(-1.0, __dmul_rn(2.0, A));
+        vw_s[r] = p.var_words[r];
+    }
+    for (int a = tid; a < p.n_inc; a += nt) {
+        uint4 rec = p.var_inc[a];
+        rec.x = rec.x * (F * 16);                     // chunk index -> byte offset
+        inc_s[a] = rec;
+    }
+    if (tid == 0) {
+        L->c.live = L->c.ran = L->c.done = L->c.fresh = 0u;
+        L->c.q_next = L->c.q_end = 0;
+        S->alive = F;
+    }
+    const double half_alpha = __dmul_rn(p.alpha, 0.5);
+    // auxiliary variables: e = 8 (two blocks x four rows)
+    const double inv_aux = __ddiv_rn(-1.0, __dmul_rn(2.0, __dmul_rn(__dadd_rn(__dmul_rn(p.mu, 8.0), -p.alpha), 0.5)));
+    // their value in iteration 0: z = yl = 0, so w = (0, 0, 0, mu (0 - 2)) in both blocks
+    double aux_init;
+    {
+        const double w3 = __fma_rn(p.mu, __dadd_rn(0.0, -2.0), 0.0);
+        double B = __dadd_rn(half_alpha, -0.0);
+        B = __dadd_rn(B, -0.0);
+        B = __dadd_rn(B, 0.0);
+        B = __dadd_rn(B, w3);
+        B = __dadd_rn(B, 0.0);
+        B = __dadd_rn(B, -0.0);
+        B = __dadd_rn(B, -0.0);
+        B = __dadd_rn(B, w3);
+        aux_init = clip01(__dmul_rn(B, inv_aux));
+    }
+
+    // ---- this lane's check (static): degree, variable offsets, chunk offsets
+    const bool has_chk = cr < p.n_chk;
+    int nb = 0;
+    uint32_t voff[NB + 2], plane_off[NB];
+#pragma unroll
+    for (int j = 0; j < NB + 2; ++j) voff[j] = 0;
+    if (has_chk) {
+        const uint32_t *tab = p.chk_tab + (size_t) cr * p.tab_stride;
+        nb = (int) tab[0] - 2;
+#pragma unroll
+        for (int j = 0; j < NB + 2; ++j)
+            if (j < nb + 2) voff[j] = (tab[1 + j] * F + f) * 8;
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) plane_off[k] = ((p.plane_base[k] + cr) * F + f) * 16;
+    double yl[NB][4], aux[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        yl[k][0] = yl[k][1] = yl[k][2] = yl[k][3] = 0.0;
+        aux[k] = aux_init;
+    }
+    __syncthreads();
+
+    for (unsigned trip = 0;; ++trip) {
+        double *vcur = v + (size_t) (trip & 1) * n_var * F;
+        const double *vprev = v + (size_t) ((trip & 1) ^ 1) * n_var * F;
+        const unsigned live = L->c.live, ran = L->c.ran;
+
+        // ---- warp 0: stop test of the previous check phase (qp_admm.h:161-163) / out of iterations
+        if (warp == 0) {
+            const int ff = lane / LPF, j = lane % LPF;
+            double sum2 = 0.0;
+            if ((ran >> ff) & 1u)
+                for (int w = j; w < nwarps; w += LPF) sum2 += red[ff * 32 + w];
+#pragma unroll
+            for (int off = LPF / 2; off >= 1; off >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
+            bool fin = false;
+            if (j == 0 && ((live >> ff) & 1u)) {
+                const int it = S->iter[ff];
+                fin = (((ran >> ff) & 1u) && sum2 < p.eps_stop) || it >= p.max_iter;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, fin);
+            unsigned done = 0;
+#pragma unroll
+            for (int q = 0; q < F; ++q) done |= ((bal >> (q * LPF)) & 1u) << q;
+            if (lane == 0) {
+                L->c.done = done;
+                L->c.fresh = 0u;      // everybody read it before the last barrier; the refill below sets it again
+            }
+        }
+
+        // ---- variable phase, qp_admm.h:132-142
+        if ((live >> f) & 1u) {
+            const char *w01_f = w01 + f * 16, *w23_f = w23 + f * 16;
+            for (int rank = cr; rank < n_var; rank += cpt) {
+                const uint32_t word = vw_s[rank];
+                const uint4 *rec = inc_s + (word >> 4);
+                const int cnt = word & 15;
+                double B = qa[rank * F + f];
+                for (int a = 0; a < cnt; ++a) {
+                    const uint4 r = rec[a];
+                    const double2 a01 = *reinterpret_cast<const double2 *>(w01_f + r.x);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(w23_f + r.x);
+                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.x) ^ (int) r.y, __double2loint(a01.x)));
+                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.y) ^ (int) r.z, __double2loint(a01.y)));
+                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a23.x) ^ (int) r.w, __double2loint(a23.x)));
+                    B = __dadd_rn(B, a23.y);
+                }
+                vcur[rank * F + f] = clip01(__dmul_rn(B, inv[rank]));
+            }
+        }
+        __syncthreads();
+
+        // ---- publish finished frames (from the previous buffer), refill their slots
+        const unsigned done = L->c.done;
+        if (done || trip == 0) {
+            for (int q = 0; q < F; ++q) {
+                if (!((done >> q) & 1u)) continue;
+                const double *vf = vprev + q;
+                int valid = 1;
+                if (io.experiment) {
+                    int bad = 0;
+                    for (int c = tid; c < io.m; c += nt) {
+                        int parity = 0;
+                        for (int e = io.row_ptr[c]; e < io.row_ptr[c + 1]; ++e)
+                            parity ^= vf[(size_t) p.var_rank[io.col_idx[e]] * F] > 0.5 ? 1 : 0;
+                        bad |= parity;
+                    }
+                    valid = !__syncthreads_or(bad);
+                }
+                slot_finish<F>(io, S, q, 1, 1, valid, S->iter[q], cw,
+                               [&](int i) { return vf[(size_t) p.var_rank[i] * F] > 0.5 ? 1 : 0; },
+                               [&](int i) { return vf[(size_t) p.var_rank[i] * F]; });
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned live_before = live & ~done;
+                const bool want = lane < F && !((live_before >> lane) & 1u) && S->state[lane] != SLOT_DEAD;
+                const unsigned wmask = __ballot_sync(0xffffffffu, want);
+                const int need = __popc(wmask), rank = __popc(wmask & ((1u << lane) - 1u));
+                const long long next = L->c.q_next, end = L->c.q_end;
+                __syncwarp();
+                const long long left = end - next;
+                long long got = 0, amt = 0;
+                if (need > left) {
+                    amt = max((long long) p.chunk, need - left);
+                    if (lane == 0) got = (long long) atomicAdd(io.queue, (unsigned long long) amt);
+                    got = __shfl_sync(0xffffffffu, got, 0);
+                }
+                if (want) {
+                    const long long fr = rank < left ? next + rank : got + (rank - left);
+                    if (fr < io.frames) { S->frame[lane] = fr; S->iter[lane] = 0; S->hamming[lane] = 0; S->state[lane] = SLOT_NEW; }
+                    else S->state[lane] = SLOT_DEAD;
+                }
+                if (lane == 0) {
+                    if (need > left) { L->c.q_next = got + (need - left); L->c.q_end = got + amt; }
+                    else L->c.q_next = next + need;
+                }
+                __syncwarp();
+                const int st = lane < F ? S->state[lane] : SLOT_DEAD;
+                const unsigned fresh = __ballot_sync(0xffffffffu, st == SLOT_NEW);
+                const unsigned dead = __ballot_sync(0xffffffffu, lane < F && st == SLOT_DEAD);
+                if (lane == 0) {
+                    L->c.fresh = fresh;
+                    L->c.live = live_before | fresh;
+                    S->alive = F - __popc(dead);
+                }
+                if (lane < F && st == SLOT_NEW) S->state[lane] = SLOT_ACTIVE;
+            }
+            __syncthreads();
+            if (S->alive == 0) break;
+            const unsigned fresh = L->c.fresh;
+            if (fresh) {
+                // z = yl = 0 (qp_admm.h:120-121): w = mu (0 - b) -- the first variable phase of the frame reads it
+                const double w3 = __fma_rn(p.mu, __dadd_rn(0.0, -2.0), 0.0);
+                for (int i = tid; i < p.n_chunks * F; i += nt)
+                    if ((fresh >> (i % F)) & 1u) {
+                        *reinterpret_cast<double2 *>(w01 + (size_t) i * 16) = make_double2(0.0, 0.0);
+                        *reinterpret_cast<double2 *>(w23 + (size_t) i * 16) = make_double2(0.0, w3);
+                    }
+                // q + alpha/2, and the v before the first update (qp_admm.h:116-119, visible only if max_iter == 0):
+                // it goes to the buffer a frame that finishes at once is published from
+                slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int q, double l) {
+                    const int r = p.var_rank[i];
+                    qa[r * F + q] = __dadd_rn(l, half_alpha);
+                    vcur[r * F + q] = l > 0.0 ? 1.0 : 0.0;
+                });
+            }
+        }
+
+        // ---- check phase, qp_admm.h:144-159, for the slots that are iterating
+        const unsigned fresh = L->c.fresh;
+        const unsigned run = live & ~done;          // had a variable phase this trip and are not finished
+        double part = 0.0;
+        if ((fresh >> f) & 1u) {                    // a new frame moved into this lane's slot: z = yl = 0
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                yl[k][0] = yl[k][1] = yl[k][2] = yl[k][3] = 0.0;
+                aux[k] = aux_init;
+            }
+        }
+        if (has_chk && ((run >> f) & 1u)) {
+            double va[NB + 2];
+            const char *vb = reinterpret_cast<const char *>(vcur);
+#pragma unroll
+            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2) ? *reinterpret_cast<const double *>(vb + voff[j]) : 0.0;
+            switch (nb) {
+                case 1: part = chk_update<1, NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                case 2: if (NB >= 2) part = chk_update<(NB >= 2 ? 2 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                case 3: if (NB >= 3) part = chk_update<(NB >= 3 ? 3 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                case 4: if (NB >= 4) part = chk_update<(NB >= 4 ? 4 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                case 5: if (NB >= 5) part = chk_update<(NB >= 5 ? 5 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                case 6: if (NB >= 6) part = chk_update<(NB >= 6 ? 6 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                default: break;
+            }
+        }
+        // the lanes of one frame are the lanes with equal lane % F
+#pragma unroll
+        for (int off = 16; off >= F; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane < F) red[lane * 32 + warp] = part;
+        if (warp == 0) {
+            if (lane < F && ((run >> lane) & 1u)) S->iter[lane] += 1;
+            if (lane == 0) L->c.ran = run;
+        }
+        __syncthreads();
+    }
+    slots_flush(io, S);
+}
+
+// ---------------------------------------------------------------- host side
+
+template <typename T>
+static int upload_chk(T **dst, const std::vector<T> &src) {
+    LDPC_CUDA(cudaMalloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+// tables of the check-centric kernel; `supported` = every check has degree 3..8 and every variable an edge
+static int get_chk_tables(const ldpc_code *c, const AdmmChkTables **out) {
+    std::lock_guard<std::mutex> lock(c->sched_mu);
+    AdmmChkTables &t = c->admm_chk;
+    if (!t.built) {
+        t.built = true;
+        t.supported = c->m > 0 && c->n < 65535;
+        for (int r = 0; r < c->m && t.supported; ++r) {
+            const int d = c->row_ptr[r + 1] - c->row_ptr[r];
+            if (d < 3 || d > CHK_MAX_NB + 2) t.supported = false;
+        }
+        for (int v = 0; v < c->n && t.supported; ++v)
+            if (c->col_ptr[v + 1] == c->col_ptr[v] || c->col_ptr[v + 1] - c->col_ptr[v] > 15) t.supported = false;
+        if (t.supported) {
+            const int m = c->m, n = c->n;
+            // checks by degree (descending, stable), variables by degree (descending, stable)
+            std::vector<int> chk(m), var(n), rank_of_var(n), rank_of_chk(m);
+            for (int i = 0; i < m; ++i) chk[i] = i;
+            for (int i = 0; i < n; ++i) var[i] = i;
+            auto cdeg = [&](int r) { return c->row_ptr[r + 1] - c->row_ptr[r]; };
+            auto vdeg = [&](int v) { return c->col_ptr[v + 1] - c->col_ptr[v]; };
+            std::stable_sort(chk.begin(), chk.end(), [&](int a, int b) { return cdeg(a) > cdeg(b); });
+            std::stable_sort(var.begin(), var.end(), [&](int a, int b) { return vdeg(a) > vdeg(b); });
+            for (int i = 0; i < n; ++i) rank_of_var[var[i]] = i;
+            for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
+            t.max_nb = cdeg(chk[0]) - 2;
+            // block k of every check that has one: a plane of consecutive chunks indexed by check rank
+            int base = 0;
+            for (int k = 0; k < CHK_MAX_NB; ++k) {
+                t.plane_base[k] = (uint32_t) base;
+                int cnt = 0;
+                for (int i = 0; i < m; ++i) cnt += cdeg(chk[i]) - 2 > k;
+                base += (cnt + 1) & ~1;            // even bases: neighbouring checks write neighbouring 64-byte rows
+            }
+            t.n_chunks = base;
+            t.tab_stride = CHK_MAX_NB + 3;
+            std::vector<uint32_t> tab((size_t) m * t.tab_stride, 0u);
+            for (int i = 0; i < m; ++i) {
+                const int r = chk[i];
+                tab[(size_t) i * t.tab_stride] = (uint32_t) cdeg(r);
+                for (int e = c->row_ptr[r], j = 0; e < c->row_ptr[r + 1]; ++e, ++j)
+                    tab[(size_t) i * t.tab_stride + 1 + j] = (uint32_t) rank_of_var[c->col_idx[e]];
+            }
+            // variable incidences in ascending row order = ascending check index (a variable is in one block per check)
+            std::vector<uint32_t> words(n);
+            std::vector<uint4> inc;
+            std::vector<uint16_t> vrank(n), ve(n);
+            int e_min = 1 << 30;
+            for (int i = 0; i < n; ++i) {
+                const int v = var[i];
+                vrank[v] = (uint16_t) i;
+                words[i] = ((uint32_t) inc.size() << 4) | (uint32_t) vdeg(v);
+                ve[i] = (uint16_t) (4 * vdeg(v));
+                e_min = std::min(e_min, 4 * vdeg(v));
+                for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) {
+                    const int e = c->csc_edge[q];
+                    const int r = (int) (std::upper_bound(c->row_ptr.begin(), c->row_ptr.end(), e) - c->row_ptr.begin()) - 1;
+                    const int d = cdeg(r), j = e - c->row_ptr[r];
+                    const int k = j == 0 ? 0 : (j == d - 1 ? d - 3 : j - 1);
+                    const int slot = j == 0 ? 0 : (j == d - 1 ? 2 : 1);
+                    uint4 rec;
+                    rec.x = t.plane_base[k] + (uint32_t) rank_of_chk[r];
+                    rec.y = slot == 0 ? 0u : 0x80000000u;
+                    rec.z = slot == 1 ? 0u : 0x80000000u;
+                    rec.w = slot == 2 ? 0u : 0x80000000u;
+                    inc.push_back(rec);
+                }
+            }
+            t.n_inc = (int) inc.size();
+            t.e_min = e_min;
+            int st;
+            if ((st = upload_chk(&t.chk_tab, tab))) return st;
+            if ((st = upload_chk(&t.var_words, words))) return st;
+            if ((st = upload_chk(&t.var_inc, inc))) return st;
+            if ((st = upload_chk(&t.var_rank, vrank))) return st;
+            if ((st = upload_chk(&t.var_e, ve))) return st;
+        }
+    }
+    *out = &t;
+    return LDPC_OK;
+}
+
+static size_t chk_smem_bytes(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment) {
+    return (size_t) 2 * t.n_chunks * F * 16 + (size_t) 3 * c->n * F * 8 + (size_t) c->n * 8 + (size_t) F * 32 * 8 +
+           (size_t) t.n_inc * 16 + (size_t) c->n * 4 + (experiment ? (size_t) F * c->n : 0) + 32 + sizeof(ChkShared<4>) + 64;
+}
+
+using ChkKernel = void (*)(const AdmmChkParams);
+
+template <int F>
+static ChkKernel chk_kernel_for(int nb) {
+    if (nb <= 2) return qpadmm_chk_kernel<F, 2>;
+    if (nb <= 4) return qpadmm_chk_kernel<F, 4>;
+    if (nb == 5) return qpadmm_chk_kernel<F, 5>;
+    return qpadmm_chk_kernel<F, 6>;
+}
+
+int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
+                      int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
+    if (frames <= 0) return LDPC_OK;
+    const AdmmChkTables *t = nullptr;
+    int st = get_chk_tables(c, &t);
+    if (st) return st;
+    if (!t->supported) return LDPC_E_UNSUPPORTED;
+    if ((double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
+    AdmmChkParams p;
+    KernelIO &io = p.io;
+    io.y = fio.y; io.bits = fio.bits; io.ok = fio.ok; io.iters = fio.iters; io.soft = fio.soft;
+    io.experiment = fio.experiment; io.cw_source = fio.cw_source; io.seed = fio.seed;
+    io.frame_begin = fio.frame_begin; io.words = fio.words; io.n_words = fio.n_words;
+    io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
+    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
+    io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
+    p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_rank = t->var_rank;
+    p.var_e = t->var_e;
+    for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
+    p.n_chk = c->m; p.n_var = c->n; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
+    p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
+
+    // frames per CTA: one lane per (check, frame), at most 640 lanes
+    int F = 4;
+    if (const char *force = getenv("LDPC_ADMM_F")) {
+        const int v = atoi(force);
+        if (v == 1 || v == 2 || v == 4) F = v;
+    } else {
+        while (F > 1 && frames < 2ll * 148 * F) F >>= 1;
+    }
+    const bool exp_mode = fio.experiment != 0;
+    while (F > 1 && (c->m * F > 640 || chk_smem_bytes(c, *t, F, exp_mode) > 227 * 1024)) F >>= 1;
+    if (c->m * F > 640 || chk_smem_bytes(c, *t, F, exp_mode) > 227 * 1024) return LDPC_E_UNSUPPORTED;
+    const int threads = (c->m * F + 31) / 32 * 32;
+    const size_t smem = chk_smem_bytes(c, *t, F, exp_mode);
+    ChkKernel fn = F == 4 ? chk_kernel_for<4>(t->max_nb) : (F == 2 ? chk_kernel_for<2>(t->max_nb) : chk_kernel_for<1>(t->max_nb));
+    LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int per_sm = 0, sms = 0;
+    LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (per_sm < 1) return LDPC_E_UNSUPPORTED;
+    const long long want = (frames + F - 1) / F;
+    const long long grid = std::min<long long>((long long) per_sm * sms, want);
+    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * 4 * F) * F));
+    fn<<<(unsigned) grid, threads, smem, stream>>>(p);
+    LDPC_CUDA(cudaGetLastError());
+    return LDPC_OK;
+}
+
+void free_chk_tables(ldpc_code *c) {
+    AdmmChkTables &t = c->admm_chk;
+    cudaFree(t.chk_tab); cudaFree(t.var_words); cudaFree(t.var_inc); cudaFree(t.var_rank); cudaFree(t.var_e);
+}
+
+}  // namespace ldpc

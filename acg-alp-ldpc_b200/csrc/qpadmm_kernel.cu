@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "admm_rows.cuh"
 #include "slots.cuh"
 
 namespace ldpc {
@@ -45,41 +46,6 @@ struct AdmmParams {
     int infeasible;   // min(e) * mu <= alpha: DecodeQPADMM returns {zeros, false} (qp_admm.h:108-114)
     double alpha, mu, eps_stop;
 };
-
-// x with its sign flipped when bit 31 of `word` is set
-__device__ __forceinline__ double flip_by(double x, uint32_t word) {
-    return __hiloint2double(__double2hiint(x) ^ (int) (word & 0x80000000u), __double2loint(x));
-}
-
-// r[q] = b[q] - sum_k cf(q, S_k) * vs[k] with the block's variables visited in
-// ascending index order; S_k = slot of the k-th visited variable; cf(q, s) = +1 if
-// q == 3 or q == s, else -1.  The leading "0 -/+ v" of rows 0..2 is folded into a
-// sign (differs from the reference only in the sign of an exact zero).
-template <int S0, int S1, int S2>
-__device__ __forceinline__ void residual_rows(double v0, double v1, double v2, double b3, double &r0, double &r1,
-                                              double &r2, double &r3) {
-    // row q: x = (q == 3 ? b3 - v0 : -+v0), then -+ v1, then -+ v2, minus where cf = +1
-    r0 = __dadd_rn(__dadd_rn(S0 == 0 ? -v0 : v0, S1 == 0 ? -v1 : v1), S2 == 0 ? -v2 : v2);
-    r1 = __dadd_rn(__dadd_rn(S0 == 1 ? -v0 : v0, S1 == 1 ? -v1 : v1), S2 == 1 ? -v2 : v2);
-    r2 = __dadd_rn(__dadd_rn(S0 == 2 ? -v0 : v0, S1 == 2 ? -v1 : v1), S2 == 2 ? -v2 : v2);
-    r3 = __dadd_rn(__dadd_rn(__dadd_rn(b3, -v0), -v1), -v2);
-}
-
-// One inequality row (qp_admm.h:154-159): yl is the dual of the previous iteration (state), r the new
-// residual.  t = r - yl; z = max(0, t); yl' = max(0, -t) (== max(0, yl - r) exactly); stop-sum term (z - r)^2;
-// w = yl' + mu (z - b).  Returns w, updates yl and part.
-template <bool ROW3>
-__device__ __forceinline__ double row_update(double r, double &yl, double &part, double mu, double b3) {
-    const double t = __dadd_rn(r, -yl);
-    // both maxima from the sign bit alone, on the integer pipe (bit-identical to std::max, signed zeros included)
-    const int hi = __double2hiint(t), lo = __double2loint(t);
-    const int neg = hi >> 31;                                          // all ones iff t < 0 (or t == -0)
-    const double z = __hiloint2double(hi & ~neg, lo & ~neg);           // max(0, t)
-    yl = __hiloint2double(hi & neg & 0x7fffffff, lo & neg);            // max(0, -t)
-    const double d = __dadd_rn(z, -r);
-    part = __fma_rn(d, d, part);
-    return __fma_rn(mu, ROW3 ? __dadd_rn(z, -b3) : z, yl);
-}
 
 template <int F, int KB>
 __global__ void __launch_bounds__(512) qpadmm_kernel(const AdmmParams p) {
@@ -361,8 +327,21 @@ static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int 
     return LDPC_OK;
 }
 
+// Decoder::decode / exp() for QP-ADMM: the check-centric kernel where it applies (all checks of degree 3..8, a
+// feasible (alpha, mu)), else the block-per-lane kernel below; LDPC_ADMM_KERNEL=block|check overrides (A/B runs).
 int launch_qpadmm(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
                   int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
+    bool chk = true;
+    if (const char *k = getenv("LDPC_ADMM_KERNEL")) chk = k[0] != 'b';
+    if (chk) {
+        const int st = launch_qpadmm_chk(c, fio, frames, var, alpha, mu, max_iter, eps_stop, queue, stream);
+        if (st != LDPC_E_UNSUPPORTED) return st;
+    }
+    return launch_qpadmm_blk(c, fio, frames, var, alpha, mu, max_iter, eps_stop, queue, stream);
+}
+
+int launch_qpadmm_blk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
+                      int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
     if (frames <= 0) return LDPC_OK;
     AdmmParams p;
     KernelIO &io = p.io;
