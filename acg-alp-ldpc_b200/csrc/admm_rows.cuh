@@ -44,6 +44,30 @@ __device__ __forceinline__ double row_update(double r, double &yl, double &part,
     return __fma_rn(mu, ROW3 ? __dadd_rn(z, -b3) : z, yl);
 }
 
+// The same row on the FP64 pipe alone (six instructions, no integer work): with s = t + |t| (= 2 max(0, t),
+// exact; the |.| is an operand modifier), z = s/2 is never formed -- every use folds the exact factor 1/2 into a
+// fused multiply-add, which rounds the same real number the reference rounds:
+//   d = z - r = fma(1/2, s, -r),   yl' = max(0, -t) = z - t = fma(1/2, s, -t)  (exact),
+//   w = yl' + mu z = fma(mu/2, s, yl'),   row 3: w = yl' + mu (z - 2) = fma(mu, fma(1/2, s, -2), yl').
+// half_mu = mu / 2 (exact).  Bit-identical to row_update (tests/test_gpu_parity.py compares v bit for bit).
+template <bool ROW3>
+__device__ __forceinline__ double row_update_fp(double r, double &yl, double &part, double mu, double half_mu) {
+    const double t = __dadd_rn(r, -yl);
+    const double s = __dadd_rn(t, fabs(t));
+    const double d = __fma_rn(0.5, s, -r);
+    part = __fma_rn(d, d, part);
+    yl = __fma_rn(0.5, s, -t);
+    return ROW3 ? __fma_rn(mu, __fma_rn(0.5, s, -2.0), yl) : __fma_rn(half_mu, s, yl);
+}
+
+// std::max(v, 0.0) then std::min(v, 1.0) (qp_admm.h:140-141) on the high word: negative (sign bit set) -> +0,
+// >= 1.0 -> 1.0, else unchanged
+__device__ __forceinline__ double clip01_int(double x) {
+    const int hi = __double2hiint(x);
+    const bool keep = (unsigned) hi < 0x3ff00000u;                     // 0 <= x < 1
+    return __hiloint2double(min(max(hi, 0), 0x3ff00000), keep ? __double2loint(x) : 0);
+}
+
 }  // namespace ldpc
 
 #endif

@@ -79,7 +79,7 @@ struct AdmmChkTables {
     uint4 *var_inc = nullptr;
     uint16_t *var_rank = nullptr, *var_e = nullptr;
     uint32_t plane_base[6] = {0, 0, 0, 0, 0, 0};
-    int n_chunks = 0, n_inc = 0, tab_stride = 0, max_nb = 0, e_min = 0;
+    int n_chunks = 0, n_inc = 0, n_slots = 0, tab_stride = 0, max_nb = 0, e_min = 0;
 };
 
 struct DeviceTables {
@@ -119,7 +119,7 @@ struct ldpc_code {
     mutable std::mutex sched_mu;
     mutable std::map<std::pair<int, int>, ldpc::BpSchedule> bp_sched;
     mutable std::map<std::pair<int, int>, ldpc::BpLrSchedule> bp_lr_sched;
-    mutable ldpc::AdmmChkTables admm_chk;
+    mutable ldpc::AdmmChkTables admm_chk[3];     // frames per CTA 1, 2, 4
 };
 
 namespace ldpc {

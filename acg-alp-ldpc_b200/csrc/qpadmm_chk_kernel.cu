@@ -34,6 +34,7 @@
 
 #include "admm_rows.cuh"
 #include "slots.cuh"
+#include "smem_ptx.cuh"
 
 namespace ldpc {
 
@@ -41,13 +42,15 @@ constexpr int CHK_MAX_NB = 6;     // blocks per check (degree <= 8)
 
 struct AdmmChkParams {
     KernelIO io;
-    const uint32_t *chk_tab;      // per check rank: (NB + 3) words: degree, then the variable RANKS of its variables (ascending variable index)
-    const uint32_t *var_words;    // per variable rank: (offset of its record in uint4 units) << 4 | incidences
+    const uint32_t *chk_tab;      // per check rank: tab_stride words: degree, then the STORAGE SLOTS of its variables (ascending variable index)
+    const uint32_t *var_words;    // per variable slot: (offset of its incidence records) << 4 | incidences; 0 = empty slot
     const uint4 *var_inc;         // incidence records {chunk index, flip mask w0, flip mask w1, flip mask w2}, row order
-    const uint16_t *var_rank;     // variable index -> rank
-    const uint16_t *var_e;        // per variable rank: sum of squared coefficients of its column (qp_admm.h:94-99)
+    const uint16_t *var_slot;     // variable index -> storage slot
+    const uint16_t *slot_e;       // per slot: sum of squared coefficients of the variable's column (qp_admm.h:94-99)
     uint32_t plane_base[CHK_MAX_NB];   // chunk index of check rank 0's k-th block
-    int n_chk, n_var, n_chunks, n_inc, tab_stride;
+    int n_chk, n_slots, n_chunks, n_inc, tab_stride;
+    // byte offsets of the arrays in dynamic shared memory
+    uint32_t off_w23, off_v, off_qa, off_inv, off_red, off_inc, off_vw, off_cw, off_ctl;
     int max_iter;
     double alpha, mu, eps_stop;
     int chunk;                    // frames claimed from the global queue at a time
@@ -67,17 +70,12 @@ struct ChkShared {
     ChkCtl c;
 };
 
-__device__ __forceinline__ double clip01(double x) {       // std::max(v, 0.0) then std::min(v, 1.0), qp_admm.h:140-141
-    x = (x < 0.0) ? 0.0 : x;
-    return (1.0 < x) ? 1.0 : x;
-}
-
 // One check with NBK blocks (degree NBK + 2), one frame.  va = the values of its variables in ascending index
 // order.  Writes the row terms of its blocks, updates yl / aux, returns the partial stop sum.
-template <int NBK, int NB, int F>
+template <int NBK, int NB>
 __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double (&yl)[NB][4], double (&aux)[NB],
-                                             char *w01, char *w23, const uint32_t (&plane_off)[NB], double mu,
-                                             double half_alpha, double inv_aux) {
+                                             uint32_t a_w01, uint32_t off_w23, const uint32_t (&plane_off)[NB],
+                                             double mu, double half_mu, double half_alpha, double inv_aux) {
     constexpr int D = NBK + 2;
     double part = 0.0, P = 0.0;
 #pragma unroll
@@ -88,12 +86,12 @@ __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double 
         else if (k == 0) residual_rows<0, 1, 2>(va[0], va[1], aux[0], 2.0, r0, r1, r2, r3);
         else if (k == NBK - 1) residual_rows<1, 2, 0>(va[D - 2], va[D - 1], aux[k - 1], 2.0, r0, r1, r2, r3);
         else residual_rows<1, 0, 2>(va[k + 1], aux[k - 1], aux[k], 2.0, r0, r1, r2, r3);
-        const double w0 = row_update<false>(r0, yl[k][0], part, mu, 2.0);
-        const double w1 = row_update<false>(r1, yl[k][1], part, mu, 2.0);
-        const double w2 = row_update<false>(r2, yl[k][2], part, mu, 2.0);
-        const double w3 = row_update<true>(r3, yl[k][3], part, mu, 2.0);
-        *reinterpret_cast<double2 *>(w01 + plane_off[k]) = make_double2(w0, w1);
-        *reinterpret_cast<double2 *>(w23 + plane_off[k]) = make_double2(w2, w3);
+        const double w0 = row_update_fp<false>(r0, yl[k][0], part, mu, half_mu);
+        const double w1 = row_update_fp<false>(r1, yl[k][1], part, mu, half_mu);
+        const double w2 = row_update_fp<false>(r2, yl[k][2], part, mu, half_mu);
+        const double w3 = row_update_fp<true>(r3, yl[k][3], part, mu, half_mu);
+        sts_f64x2(a_w01 + plane_off[k], w0, w1);
+        sts_f64x2(a_w01 + off_w23 + plane_off[k], w2, w3);
         // the auxiliary variable between blocks k-1 and k, for the next iteration (qp_admm.h:132-142 with q = 0):
         // rows of block k-1 (slot 2: -,-,+,+) then rows of block k (slot 0: +,-,-,+)
         if (k > 0) {
@@ -101,7 +99,7 @@ __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double 
             B = __dadd_rn(B, -w1);
             B = __dadd_rn(B, -w2);
             B = __dadd_rn(B, w3);
-            aux[k - 1] = clip01(__dmul_rn(B, inv_aux));
+            aux[k - 1] = clip01_int(__dmul_rn(B, inv_aux));
         }
         if (k < NBK - 1) {
             P = __dadd_rn(half_alpha, -w0);
@@ -117,44 +115,40 @@ template <int F, int NB>
 __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
-    const int n = io.n, n_var = p.n_var;
+    const int n = io.n;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int warp = tid >> 5, nwarps = nt >> 5, lane = tid & 31;
-    const int f = tid % F, cr = tid / F;              // this lane's frame slot and check rank (static)
-    const int cpt = nt / F;                           // variable ranks between the steps of a lane
+    const int f = tid % F, cr = tid / F;              // this lane's frame slot and check rank / variable column (static)
+    const int cpt = nt / F;                           // variable slots between the steps of a lane
     constexpr int LPF = 32 / F;                       // lanes of one frame in a warp
 
-    char *w01 = reinterpret_cast<char *>(smem);                        // n_chunks x F x 16 B
-    char *w23 = w01 + (size_t) p.n_chunks * F * 16;
-    double *v = reinterpret_cast<double *>(w23 + (size_t) p.n_chunks * F * 16);   // 2 x n_var x F
-    double *qa = v + (size_t) 2 * n_var * F;                           // n_var x F: q_i + alpha/2
-    double *inv = qa + (size_t) n_var * F;                             // n_var: -1 / (mu e_i - alpha)
-    double *red = inv + n_var;                                         // F x 32 partial stop sums
-    uint4 *inc_s = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(red + F * 32) + 15) & ~(uintptr_t) 15);   // incidence records
-    uint32_t *vw_s = reinterpret_cast<uint32_t *>(inc_s + p.n_inc);    // variable words
-    uint8_t *cw = reinterpret_cast<uint8_t *>(vw_s + n_var);           // F x n (experiment mode)
-    ChkShared<F> *L = reinterpret_cast<ChkShared<F> *>(
-        (reinterpret_cast<uintptr_t>(cw + (io.experiment ? (size_t) n * F : 0)) + 15) & ~(uintptr_t) 15);
+    char *sm = reinterpret_cast<char *>(smem);
+    const uint32_t sbase = smem_addr(smem);
+    uint8_t *cw = reinterpret_cast<uint8_t *>(sm + p.off_cw);          // F x n (experiment mode)
+    ChkShared<F> *L = reinterpret_cast<ChkShared<F> *>(sm + p.off_ctl);
     SlotBlock<F> *S = &L->S;
+    double *v_gen = reinterpret_cast<double *>(sm + p.off_v);          // generic views for the cold paths
+    double *qa_gen = reinterpret_cast<double *>(sm + p.off_qa);
+    double *red_gen = reinterpret_cast<double *>(sm + p.off_red);
 
     slots_init(S);
     // inv_coef, qp_admm.h:123-127 (A = (mu e - alpha)/2; inv = -1/(2A))
-    for (int r = tid; r < n_var; r += nt) {
-        const double A = __dmul_rn(__dadd_rn(__dmul_rn(p.mu, (double) p.var_e[r]), -p.alpha), 0.5);
-        inv[r] = __ddiv_rn(-1.0, __dmul_rn(2.0, A));
-        vw_s[r] = p.var_words[r];
+    for (int r = tid; r < p.n_slots; r += nt) {
+        const double A = __dmul_rn(__dadd_rn(__dmul_rn(p.mu, (double) p.slot_e[r]), -p.alpha), 0.5);
+        reinterpret_cast<double *>(sm + p.off_inv)[r] = __ddiv_rn(-1.0, __dmul_rn(2.0, A));
+        reinterpret_cast<uint32_t *>(sm + p.off_vw)[r] = p.var_words[r];
     }
     for (int a = tid; a < p.n_inc; a += nt) {
         uint4 rec = p.var_inc[a];
         rec.x = rec.x * (F * 16);                     // chunk index -> byte offset
-        inc_s[a] = rec;
+        reinterpret_cast<uint4 *>(sm + p.off_inc)[a] = rec;
     }
     if (tid == 0) {
         L->c.live = L->c.ran = L->c.done = L->c.fresh = 0u;
         L->c.q_next = L->c.q_end = 0;
         S->alive = F;
     }
-    const double half_alpha = __dmul_rn(p.alpha, 0.5);
+    const double half_alpha = __dmul_rn(p.alpha, 0.5), half_mu = __dmul_rn(p.mu, 0.5);
     // auxiliary variables: e = 8 (two blocks x four rows)
     const double inv_aux = __ddiv_rn(-1.0, __dmul_rn(2.0, __dmul_rn(__dadd_rn(__dmul_rn(p.mu, 8.0), -p.alpha), 0.5)));
     // their value in iteration 0: z = yl = 0, so w = (0, 0, 0, mu (0 - 2)) in both blocks
@@ -169,7 +163,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         B = __dadd_rn(B, -0.0);
         B = __dadd_rn(B, -0.0);
         B = __dadd_rn(B, w3);
-        aux_init = clip01(__dmul_rn(B, inv_aux));
+        aux_init = clip01_int(__dmul_rn(B, inv_aux));
     }
 
     // ---- this lane's check (static): degree, variable offsets, chunk offsets
@@ -183,21 +177,28 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         nb = (int) tab[0] - 2;
 #pragma unroll
         for (int j = 0; j < NB + 2; ++j)
-            if (j < nb + 2) voff[j] = (tab[1 + j] * F + f) * 8;
+            if (j < nb + 2) voff[j] = tab[1 + j] * (F * 8);
     }
 #pragma unroll
-    for (int k = 0; k < NB; ++k) plane_off[k] = ((p.plane_base[k] + cr) * F + f) * 16;
+    for (int k = 0; k < NB; ++k) plane_off[k] = (p.plane_base[k] + cr) * (F * 16);
     double yl[NB][4], aux[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
         yl[k][0] = yl[k][1] = yl[k][2] = yl[k][3] = 0.0;
         aux[k] = aux_init;
     }
+    // shared-window addresses of this lane's frame column
+    const uint32_t a_w01 = sbase + f * 16;                          // + chunk * F * 16 (w23: + off_w23)
+    const uint32_t a_v0 = sbase + p.off_v + f * 8;                  // + slot * F * 8   (second buffer: + vbuf)
+    const uint32_t vbuf = (uint32_t) p.n_slots * F * 8;
+    const uint32_t a_qa = sbase + p.off_qa + f * 8;
+    const uint32_t a_inv = sbase + p.off_inv, a_inc = sbase + p.off_inc, a_vw = sbase + p.off_vw;
     __syncthreads();
 
     for (unsigned trip = 0;; ++trip) {
-        double *vcur = v + (size_t) (trip & 1) * n_var * F;
-        const double *vprev = v + (size_t) ((trip & 1) ^ 1) * n_var * F;
+        const uint32_t a_vcur = a_v0 + ((trip & 1) ? vbuf : 0u);
+        double *vcur_gen = v_gen + (size_t) (trip & 1) * p.n_slots * F;
+        const double *vprev_gen = v_gen + (size_t) ((trip & 1) ^ 1) * p.n_slots * F;
         const unsigned live = L->c.live, ran = L->c.ran;
 
         // ---- warp 0: stop test of the previous check phase (qp_admm.h:161-163) / out of iterations
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
             const int ff = lane / LPF, j = lane % LPF;
             double sum2 = 0.0;
             if ((ran >> ff) & 1u)
-                for (int w = j; w < nwarps; w += LPF) sum2 += red[ff * 32 + w];
+                for (int w = j; w < nwarps; w += LPF) sum2 += red_gen[ff * 32 + w];
 #pragma unroll
             for (int off = LPF / 2; off >= 1; off >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
             bool fin = false;
@@ -223,24 +224,23 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
             }
         }
 
-        // ---- variable phase, qp_admm.h:132-142
+        // ---- variable phase, qp_admm.h:132-142: this lane's column of variable slots
         if ((live >> f) & 1u) {
-            const char *w01_f = w01 + f * 16, *w23_f = w23 + f * 16;
-            for (int rank = cr; rank < n_var; rank += cpt) {
-                const uint32_t word = vw_s[rank];
-                const uint4 *rec = inc_s + (word >> 4);
-                const int cnt = word & 15;
-                double B = qa[rank * F + f];
-                for (int a = 0; a < cnt; ++a) {
-                    const uint4 r = rec[a];
-                    const double2 a01 = *reinterpret_cast<const double2 *>(w01_f + r.x);
-                    const double2 a23 = *reinterpret_cast<const double2 *>(w23_f + r.x);
+            for (int slot = cr; slot < p.n_slots; slot += cpt) {
+                const uint32_t word = lds_u32(a_vw + slot * 4);
+                if (word == 0u) continue;                               // empty slot
+                uint32_t rec = a_inc + (word >> 4) * 16;
+                const uint32_t rec_end = rec + (word & 15u) * 16;
+                double B = lds_f64(a_qa + slot * (F * 8));
+                for (; rec != rec_end; rec += 16) {
+                    const uint4 r = lds_u32x4(rec);
+                    const double2 a01 = lds_f64x2(a_w01 + r.x), a23 = lds_f64x2(a_w01 + p.off_w23 + r.x);
                     B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.x) ^ (int) r.y, __double2loint(a01.x)));
                     B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.y) ^ (int) r.z, __double2loint(a01.y)));
                     B = __dadd_rn(B, __hiloint2double(__double2hiint(a23.x) ^ (int) r.w, __double2loint(a23.x)));
                     B = __dadd_rn(B, a23.y);
                 }
-                vcur[rank * F + f] = clip01(__dmul_rn(B, inv[rank]));
+                sts_f64(a_vcur + slot * (F * 8), clip01_int(__dmul_rn(B, lds_f64(a_inv + slot * 8))));
             }
         }
         __syncthreads();
@@ -250,21 +250,21 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         if (done || trip == 0) {
             for (int q = 0; q < F; ++q) {
                 if (!((done >> q) & 1u)) continue;
-                const double *vf = vprev + q;
+                const double *vf = vprev_gen + q;
                 int valid = 1;
                 if (io.experiment) {
                     int bad = 0;
                     for (int c = tid; c < io.m; c += nt) {
                         int parity = 0;
                         for (int e = io.row_ptr[c]; e < io.row_ptr[c + 1]; ++e)
-                            parity ^= vf[(size_t) p.var_rank[io.col_idx[e]] * F] > 0.5 ? 1 : 0;
+                            parity ^= vf[(size_t) p.var_slot[io.col_idx[e]] * F] > 0.5 ? 1 : 0;
                         bad |= parity;
                     }
                     valid = !__syncthreads_or(bad);
                 }
                 slot_finish<F>(io, S, q, 1, 1, valid, S->iter[q], cw,
-                               [&](int i) { return vf[(size_t) p.var_rank[i] * F] > 0.5 ? 1 : 0; },
-                               [&](int i) { return vf[(size_t) p.var_rank[i] * F]; });
+                               [&](int i) { return vf[(size_t) p.var_slot[i] * F] > 0.5 ? 1 : 0; },
+                               [&](int i) { return vf[(size_t) p.var_slot[i] * F]; });
             }
             __syncthreads();
             if (warp == 0) {
@@ -309,15 +309,15 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                 const double w3 = __fma_rn(p.mu, __dadd_rn(0.0, -2.0), 0.0);
                 for (int i = tid; i < p.n_chunks * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) {
-                        *reinterpret_cast<double2 *>(w01 + (size_t) i * 16) = make_double2(0.0, 0.0);
-                        *reinterpret_cast<double2 *>(w23 + (size_t) i * 16) = make_double2(0.0, w3);
+                        sts_f64x2(sbase + i * 16, 0.0, 0.0);
+                        sts_f64x2(sbase + p.off_w23 + i * 16, 0.0, w3);
                     }
                 // q + alpha/2, and the v before the first update (qp_admm.h:116-119, visible only if max_iter == 0):
                 // it goes to the buffer a frame that finishes at once is published from
                 slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int q, double l) {
-                    const int r = p.var_rank[i];
-                    qa[r * F + q] = __dadd_rn(l, half_alpha);
-                    vcur[r * F + q] = l > 0.0 ? 1.0 : 0.0;
+                    const int r = p.var_slot[i];
+                    qa_gen[r * F + q] = __dadd_rn(l, half_alpha);
+                    vcur_gen[r * F + q] = l > 0.0 ? 1.0 : 0.0;
                 });
             }
         }
@@ -335,23 +335,24 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         }
         if (has_chk && ((run >> f) & 1u)) {
             double va[NB + 2];
-            const char *vb = reinterpret_cast<const char *>(vcur);
 #pragma unroll
-            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2) ? *reinterpret_cast<const double *>(vb + voff[j]) : 0.0;
+            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2) ? lds_f64(a_vcur + voff[j]) : 0.0;
+#define LDPC_CHK_CASE(K)                                                                                          \
+    case K:                                                                                                       \
+        if (NB >= K)                                                                                              \
+            part = chk_update<(NB >= K ? K : 1), NB>(va, yl, aux, a_w01, p.off_w23, plane_off, p.mu, half_mu,     \
+                                                     half_alpha, inv_aux);                                        \
+        break;
             switch (nb) {
-                case 1: part = chk_update<1, NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
-                case 2: if (NB >= 2) part = chk_update<(NB >= 2 ? 2 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
-                case 3: if (NB >= 3) part = chk_update<(NB >= 3 ? 3 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
-                case 4: if (NB >= 4) part = chk_update<(NB >= 4 ? 4 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
-                case 5: if (NB >= 5) part = chk_update<(NB >= 5 ? 5 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
-                case 6: if (NB >= 6) part = chk_update<(NB >= 6 ? 6 : 1), NB, F>(va, yl, aux, w01, w23, plane_off, p.mu, half_alpha, inv_aux); break;
+                LDPC_CHK_CASE(1) LDPC_CHK_CASE(2) LDPC_CHK_CASE(3) LDPC_CHK_CASE(4) LDPC_CHK_CASE(5) LDPC_CHK_CASE(6)
                 default: break;
             }
+#undef LDPC_CHK_CASE
         }
         // the lanes of one frame are the lanes with equal lane % F
 #pragma unroll
         for (int off = 16; off >= F; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        if (lane < F) red[lane * 32 + warp] = part;
+        if (lane < F) red_gen[lane * 32 + warp] = part;
         if (warp == 0) {
             if (lane < F && ((run >> lane) & 1u)) S->iter[lane] += 1;
             if (lane == 0) L->c.ran = run;
@@ -370,10 +371,13 @@ static int upload_chk(T **dst, const std::vector<T> &src) {
     return LDPC_OK;
 }
 
-// tables of the check-centric kernel; `supported` = every check has degree 3..8 and every variable an edge
-static int get_chk_tables(const ldpc_code *c, const AdmmChkTables **out) {
+static int chk_threads(const ldpc_code *c, int F) { return (c->m * F + 31) / 32 * 32; }
+
+// Tables of the check-centric kernel for F frames per CTA (the variable slots depend on the CTA's column count);
+// `supported` = every check has degree 3..8 and every variable 1..15 edges.
+static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) {
     std::lock_guard<std::mutex> lock(c->sched_mu);
-    AdmmChkTables &t = c->admm_chk;
+    AdmmChkTables &t = c->admm_chk[F == 4 ? 2 : (F == 2 ? 1 : 0)];
     if (!t.built) {
         t.built = true;
         t.supported = c->m > 0 && c->n < 65535;
@@ -386,23 +390,36 @@ static int get_chk_tables(const ldpc_code *c, const AdmmChkTables **out) {
         if (t.supported) {
             const int m = c->m, n = c->n;
             // checks by degree (descending, stable), variables by degree (descending, stable)
-            std::vector<int> chk(m), var(n), rank_of_var(n), rank_of_chk(m);
+            std::vector<int> chk(m), var(n), rank_of_chk(m);
             for (int i = 0; i < m; ++i) chk[i] = i;
             for (int i = 0; i < n; ++i) var[i] = i;
             auto cdeg = [&](int r) { return c->row_ptr[r + 1] - c->row_ptr[r]; };
             auto vdeg = [&](int v) { return c->col_ptr[v + 1] - c->col_ptr[v]; };
             std::stable_sort(chk.begin(), chk.end(), [&](int a, int b) { return cdeg(a) > cdeg(b); });
             std::stable_sort(var.begin(), var.end(), [&](int a, int b) { return vdeg(a) > vdeg(b); });
-            for (int i = 0; i < n; ++i) rank_of_var[var[i]] = i;
             for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
             t.max_nb = cdeg(chk[0]) - 2;
+            // Variable slots: lane column c of the CTA updates the slots c, c + cols, c + 2 cols, ...  The variables
+            // are dealt to the columns in boustrophedon order, heaviest first, so that every column gets about the
+            // same number of incidences (the variable phase ends at a barrier) and neighbouring columns -- the lanes
+            // of one warp -- get variables of equal degree.
+            const int cols = chk_threads(c, F) / F;
+            const int steps = (n + cols - 1) / cols;
+            t.n_slots = steps * cols;
+            std::vector<int> slot_of_var(n, 0), var_of_slot(t.n_slots, -1);
+            for (int i = 0; i < n; ++i) {
+                const int j = i / cols, k = i % cols;
+                const int col = (j & 1) ? cols - 1 - k : k;
+                slot_of_var[var[i]] = j * cols + col;
+                var_of_slot[j * cols + col] = var[i];
+            }
             // block k of every check that has one: a plane of consecutive chunks indexed by check rank
             int base = 0;
             for (int k = 0; k < CHK_MAX_NB; ++k) {
                 t.plane_base[k] = (uint32_t) base;
                 int cnt = 0;
                 for (int i = 0; i < m; ++i) cnt += cdeg(chk[i]) - 2 > k;
-                base += (cnt + 1) & ~1;            // even bases: neighbouring checks write neighbouring 64-byte rows
+                base += (cnt + 1) & ~1;            // even bases: neighbouring checks write neighbouring rows
             }
             t.n_chunks = base;
             t.tab_stride = CHK_MAX_NB + 3;
@@ -411,18 +428,19 @@ static int get_chk_tables(const ldpc_code *c, const AdmmChkTables **out) {
                 const int r = chk[i];
                 tab[(size_t) i * t.tab_stride] = (uint32_t) cdeg(r);
                 for (int e = c->row_ptr[r], j = 0; e < c->row_ptr[r + 1]; ++e, ++j)
-                    tab[(size_t) i * t.tab_stride + 1 + j] = (uint32_t) rank_of_var[c->col_idx[e]];
+                    tab[(size_t) i * t.tab_stride + 1 + j] = (uint32_t) slot_of_var[c->col_idx[e]];
             }
             // variable incidences in ascending row order = ascending check index (a variable is in one block per check)
-            std::vector<uint32_t> words(n);
+            std::vector<uint32_t> words(t.n_slots, 0u);
             std::vector<uint4> inc;
-            std::vector<uint16_t> vrank(n), ve(n);
+            std::vector<uint16_t> vslot(n), se(t.n_slots, 4);
             int e_min = 1 << 30;
-            for (int i = 0; i < n; ++i) {
-                const int v = var[i];
-                vrank[v] = (uint16_t) i;
-                words[i] = ((uint32_t) inc.size() << 4) | (uint32_t) vdeg(v);
-                ve[i] = (uint16_t) (4 * vdeg(v));
+            for (int sl = 0; sl < t.n_slots; ++sl) {
+                const int v = var_of_slot[sl];
+                if (v < 0) continue;
+                vslot[v] = (uint16_t) sl;
+                words[sl] = ((uint32_t) inc.size() << 4) | (uint32_t) vdeg(v);
+                se[sl] = (uint16_t) (4 * vdeg(v));
                 e_min = std::min(e_min, 4 * vdeg(v));
                 for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) {
                     const int e = c->csc_edge[q];
@@ -444,17 +462,35 @@ static int get_chk_tables(const ldpc_code *c, const AdmmChkTables **out) {
             if ((st = upload_chk(&t.chk_tab, tab))) return st;
             if ((st = upload_chk(&t.var_words, words))) return st;
             if ((st = upload_chk(&t.var_inc, inc))) return st;
-            if ((st = upload_chk(&t.var_rank, vrank))) return st;
-            if ((st = upload_chk(&t.var_e, ve))) return st;
+            if ((st = upload_chk(&t.var_rank, vslot))) return st;
+            if ((st = upload_chk(&t.var_e, se))) return st;
         }
     }
     *out = &t;
     return LDPC_OK;
 }
 
-static size_t chk_smem_bytes(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment) {
-    return (size_t) 2 * t.n_chunks * F * 16 + (size_t) 3 * c->n * F * 8 + (size_t) c->n * 8 + (size_t) F * 32 * 8 +
-           (size_t) t.n_inc * 16 + (size_t) c->n * 4 + (experiment ? (size_t) F * c->n : 0) + 32 + sizeof(ChkShared<4>) + 64;
+static size_t up16(size_t x) { return (x + 15) & ~(size_t) 15; }
+
+// carve-up of the dynamic shared memory; returns the total
+static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment, AdmmChkParams *p) {
+    size_t off = 0;
+    off += (size_t) t.n_chunks * F * 16;                 // w01
+    const size_t off_w23 = off; off += (size_t) t.n_chunks * F * 16;
+    const size_t off_v = off; off += (size_t) 2 * t.n_slots * F * 8;
+    const size_t off_qa = off; off += (size_t) t.n_slots * F * 8;
+    const size_t off_inv = off; off += (size_t) t.n_slots * 8;
+    const size_t off_red = off; off += (size_t) F * 32 * 8;
+    const size_t off_inc = up16(off); off = off_inc + (size_t) t.n_inc * 16;
+    const size_t off_vw = off; off += (size_t) t.n_slots * 4;
+    const size_t off_cw = off; off += experiment ? (size_t) F * c->n : 0;
+    const size_t off_ctl = up16(off); off = off_ctl + sizeof(ChkShared<4>);
+    if (p) {
+        p->off_w23 = (uint32_t) off_w23; p->off_v = (uint32_t) off_v; p->off_qa = (uint32_t) off_qa;
+        p->off_inv = (uint32_t) off_inv; p->off_red = (uint32_t) off_red; p->off_inc = (uint32_t) off_inc;
+        p->off_vw = (uint32_t) off_vw; p->off_cw = (uint32_t) off_cw; p->off_ctl = (uint32_t) off_ctl;
+    }
+    return off + 16;
 }
 
 using ChkKernel = void (*)(const AdmmChkParams);
@@ -470,25 +506,6 @@ static ChkKernel chk_kernel_for(int nb) {
 int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
                       int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
     if (frames <= 0) return LDPC_OK;
-    const AdmmChkTables *t = nullptr;
-    int st = get_chk_tables(c, &t);
-    if (st) return st;
-    if (!t->supported) return LDPC_E_UNSUPPORTED;
-    if ((double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
-    AdmmChkParams p;
-    KernelIO &io = p.io;
-    io.y = fio.y; io.bits = fio.bits; io.ok = fio.ok; io.iters = fio.iters; io.soft = fio.soft;
-    io.experiment = fio.experiment; io.cw_source = fio.cw_source; io.seed = fio.seed;
-    io.frame_begin = fio.frame_begin; io.words = fio.words; io.n_words = fio.n_words;
-    io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
-    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
-    io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
-    p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_rank = t->var_rank;
-    p.var_e = t->var_e;
-    for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
-    p.n_chk = c->m; p.n_var = c->n; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
-    p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
-
     // frames per CTA: one lane per (check, frame), at most 640 lanes
     int F = 4;
     if (const char *force = getenv("LDPC_ADMM_F")) {
@@ -498,10 +515,30 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
         while (F > 1 && frames < 2ll * 148 * F) F >>= 1;
     }
     const bool exp_mode = fio.experiment != 0;
-    while (F > 1 && (c->m * F > 640 || chk_smem_bytes(c, *t, F, exp_mode) > 227 * 1024)) F >>= 1;
-    if (c->m * F > 640 || chk_smem_bytes(c, *t, F, exp_mode) > 227 * 1024) return LDPC_E_UNSUPPORTED;
-    const int threads = (c->m * F + 31) / 32 * 32;
-    const size_t smem = chk_smem_bytes(c, *t, F, exp_mode);
+    const AdmmChkTables *t = nullptr;
+    for (;; F >>= 1) {
+        int st = get_chk_tables(c, F, &t);
+        if (st) return st;
+        if (!t->supported) return LDPC_E_UNSUPPORTED;
+        if (c->m * F <= 640 && chk_smem_layout(c, *t, F, exp_mode, nullptr) <= 227 * 1024) break;
+        if (F == 1) return LDPC_E_UNSUPPORTED;
+    }
+    if ((double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
+    AdmmChkParams p;
+    KernelIO &io = p.io;
+    io.y = fio.y; io.bits = fio.bits; io.ok = fio.ok; io.iters = fio.iters; io.soft = fio.soft;
+    io.experiment = fio.experiment; io.cw_source = fio.cw_source; io.seed = fio.seed;
+    io.frame_begin = fio.frame_begin; io.words = fio.words; io.n_words = fio.n_words;
+    io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
+    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
+    io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
+    p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_slot = t->var_rank;
+    p.slot_e = t->var_e;
+    for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
+    p.n_chk = c->m; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
+    p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
+    const int threads = chk_threads(c, F);
+    const size_t smem = chk_smem_layout(c, *t, F, exp_mode, &p);
     ChkKernel fn = F == 4 ? chk_kernel_for<4>(t->max_nb) : (F == 2 ? chk_kernel_for<2>(t->max_nb) : chk_kernel_for<1>(t->max_nb));
     LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
@@ -517,8 +554,9 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
 }
 
 void free_chk_tables(ldpc_code *c) {
-    AdmmChkTables &t = c->admm_chk;
-    cudaFree(t.chk_tab); cudaFree(t.var_words); cudaFree(t.var_inc); cudaFree(t.var_rank); cudaFree(t.var_e);
+    for (AdmmChkTables &t : c->admm_chk) {
+        cudaFree(t.chk_tab); cudaFree(t.var_words); cudaFree(t.var_inc); cudaFree(t.var_rank); cudaFree(t.var_e);
+    }
 }
 
 }  // namespace ldpc

@@ -1,0 +1,43 @@
+// Shared-memory accesses through 32-bit shared-window addresses (inline PTX).  With ordinary pointers nvcc loses the
+// address space of anything derived from a runtime-sized carve-up of the dynamic shared array and falls back to
+// generic loads plus window arithmetic (six instructions per access, profiles/r01_admm_chk_v1_ncu.txt); a 32-bit
+// address is one register, and an LDS / STS takes register + immediate.
+#ifndef LDPC_B200_SMEM_PTX_CUH
+#define LDPC_B200_SMEM_PTX_CUH
+
+#include <cstdint>
+
+namespace ldpc {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+}  // namespace ldpc
+
+#endif
