@@ -506,8 +506,9 @@ static ChkKernel chk_kernel_for(int nb) {
 int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
                       int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
     if (frames <= 0) return LDPC_OK;
-    // frames per CTA: one lane per (check, frame), at most 640 lanes
-    int F = 4;
+    // frames per CTA: one lane per (check, frame), at most 640 lanes.  Two CTAs of two frames per SM beat one CTA
+    // of four (profiles/r01_admm_chk_sweep.txt): their barriers and their FP64-bound / latency-bound phases overlap.
+    int F = 2;
     if (const char *force = getenv("LDPC_ADMM_F")) {
         const int v = atoi(force);
         if (v == 1 || v == 2 || v == 4) F = v;

@@ -39,7 +39,8 @@ ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
 BP_FP64_PER_EDGE_ITER = 12.0          # check: 5.3 Pe/Po recurrences + 5 division; variable: 2.7 products + decision
 BP_SMEM_BYTES_PER_EDGE_ITER = 32.0    # each message is read and written once per pass (8 B), two passes
 BP_SMEM_BYTES_PER_VAR_ITER = 8.0      # channel likelihood ratio
-ADMM_FP64_PER_BLOCK_ITER = 42.0       # 12 gather adds + 9 residual + 17 row updates (4 t, 4 d, 1 zb, 8 fma) + 4 v ops
+# QP-ADMM, check-centric kernel: per three-variable block and iteration
+ADMM_FP64_PER_BLOCK_ITER = 47.0       # 9 residual + 25 row updates (6 per row, 7 for row 3) + 6.5 auxiliary update + 6.5 variable update
 
 
 def peaks():
@@ -313,9 +314,11 @@ def run_gpu(args):
             "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),
         }
         if algo == "qpadmm":
-            # the QP-ADMM iteration is bound by shared-memory bandwidth before the FP64 pipe: algorithmic bytes per
-            # frame-iteration = gathers of w (nnz x 8) and v (3 x 8 per block) + stores of w (rows x 8) and v
-            smem_bytes = info["admm_nnz"] * 8 + info["admm_blocks"] * 24 + info["admm_rows"] * 8 + info["admm_n_var"] * 8
+            # shared-memory traffic of the check-centric kernel per frame-iteration: the row terms w are written once
+            # per block (32 B) and gathered once per (original variable, check) incidence (32 B); v is written once
+            # per original variable and gathered once per incidence (8 B); q + alpha/2 and inv_coef are read per variable
+            inc = info["edges"]
+            smem_bytes = info["admm_blocks"] * 32 + inc * 32 + inc * 8 + info["n"] * 24
             got = fps_gpu * n_iter * smem_bytes / 1e9
             res["roofline"]["smem"] = {"achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
                                        "bytes_per_frame_iter": smem_bytes,
