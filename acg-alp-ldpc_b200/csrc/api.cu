@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <vector>
 
 #include "ldpc_internal.h"
 
@@ -268,6 +269,91 @@ int ldpc_experiment_run(const ldpc_code_t *c, const ldpc_algo_cfg_t *cfg, double
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d_words);
+    return st;
+}
+
+int ldpc_qpadmm_grid_run(const ldpc_code_t *c, int32_t points, const double *alpha, const double *mu,
+                         int32_t max_iter, double eps_stop, double snr, uint64_t seed, uint64_t frame_begin,
+                         uint64_t frame_count, int32_t codeword_source, const uint8_t *words, uint64_t n_words,
+                         uint64_t *counters, double *gpu_seconds) {
+    if (!c || !alpha || !mu || !counters || points < 0) return fail(LDPC_E_INVALID, "bad argument");
+    if (max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
+    if (gpu_seconds) *gpu_seconds = 0.0;
+    for (int64_t i = 0; i < (int64_t) points * LDPC_CNT_COUNT; ++i) counters[i] = 0;
+    if (points == 0 || frame_count == 0) return LDPC_OK;
+    // pairs the check-centric kernel cannot take (infeasible, or a code outside its range) run one by one
+    const int e_min = qpadmm_chk_e_min(c);
+    std::vector<int> batch;
+    std::vector<double> ba, bm;
+    ldpc_algo_cfg_t cfg{LDPC_ALGO_QPADMM, max_iter, 1, 0, alpha[0], mu[0], eps_stop};
+    for (int i = 0; i < points; ++i) {
+        if (e_min > 0 && (double) e_min * mu[i] > alpha[i]) {
+            batch.push_back(i); ba.push_back(alpha[i]); bm.push_back(mu[i]);
+            continue;
+        }
+        cfg.alpha = alpha[i]; cfg.mu = mu[i];
+        double secs = 0;
+        int st = ldpc_experiment_run(c, &cfg, snr, seed, frame_begin, frame_count, codeword_source, words, n_words,
+                                     counters + (size_t) i * LDPC_CNT_COUNT, &secs);
+        if (st) return st;
+        if (gpu_seconds) *gpu_seconds += secs;
+    }
+    if (batch.empty()) return LDPC_OK;
+    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
+        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
+    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
+        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
+    LDPC_CUDA(cudaSetDevice(c->device));
+    Slot &s = g_ctx.per_device[c->device][0];
+    int st = slot_init(s);
+    if (st) return st;
+    const size_t nb = batch.size();
+    uint8_t *d_words = nullptr;
+    double *d_par = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<unsigned long long> host_cnt(nb * LDPC_CNT_COUNT);
+    auto cleanup = [&]() {
+        cudaFree(d_words); cudaFree(d_par); cudaFree(d_cnt);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    cudaError_t e = cudaSuccess;
+    if (codeword_source == LDPC_CW_TABLE) {
+        e = cudaMalloc((void **) &d_words, n_words * (size_t) c->n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void **) &d_par, sizeof(double) * 2 * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, sizeof(unsigned long long) * nb * LDPC_CNT_COUNT);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, ba.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + nb, bm.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nb * LDPC_CNT_COUNT, s.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s.queue, 0, sizeof(unsigned long long), s.stream);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "grid setup", __FILE__, __LINE__); }
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    FrameIO io;
+    io.experiment = 1; io.seed = seed; io.frame_begin = frame_begin; io.cw_source = codeword_source;
+    io.words = d_words; io.n_words = n_words; io.counters = d_cnt;
+    cudaEventRecord(e0, s.stream);
+    st = launch_qpadmm_chk(c, io, (int64_t) frame_count, llr_variance(snr), ba[0], bm[0], max_iter, eps_stop, s.queue,
+                           s.stream, d_par, d_par + nb, (int64_t) nb);
+    cudaEventRecord(e1, s.stream);
+    if (st == LDPC_E_UNSUPPORTED) st = fail(LDPC_E_UNSUPPORTED, "grid launch: code outside the check-centric kernel's range");
+    if (!st) {
+        e = cudaMemcpyAsync(host_cnt.data(), d_cnt, sizeof(unsigned long long) * host_cnt.size(), cudaMemcpyDeviceToHost, s.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "grid run", __FILE__, __LINE__);
+    }
+    if (!st) {
+        for (size_t b = 0; b < nb; ++b)
+            for (int k = 0; k < LDPC_CNT_COUNT; ++k)
+                counters[(size_t) batch[b] * LDPC_CNT_COUNT + k] = host_cnt[b * LDPC_CNT_COUNT + k];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (gpu_seconds) *gpu_seconds += ms * 1e-3;
+    }
+    cleanup();
     return st;
 }
 

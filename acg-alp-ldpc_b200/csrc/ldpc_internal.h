@@ -154,8 +154,11 @@ double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
 // the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 3..8) and block-per-lane (any code)
+// grid_points > 0: `frames` frames under each of grid_points (alpha, mu) pairs (device arrays), counters per point
 int launch_qpadmm_chk(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
-                      double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
+                      double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream,
+                      const double *grid_alpha = nullptr, const double *grid_mu = nullptr, int64_t grid_points = 0);
+int qpadmm_chk_e_min(const ldpc_code *code);
 int launch_qpadmm_blk(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                       double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
 void free_chk_tables(ldpc_code *code);

@@ -54,6 +54,10 @@ struct AdmmChkParams {
     int max_iter;
     double alpha, mu, eps_stop;
     int chunk;                    // frames claimed from the global queue at a time
+    // grid mode (qpadmm_params.cpp:51-67): work item q of the queue = frame q % grid_frames under the parameters of
+    // point q / grid_frames; counters per point
+    const double *grid_alpha, *grid_mu;
+    long long grid_frames;
 };
 
 struct ChkCtl {
@@ -68,6 +72,9 @@ template <int F>
 struct ChkShared {
     SlotBlock<F> S;
     ChkCtl c;
+    double alpha[F], mu[F];       // grid mode: parameters of the slot's work item
+    double inv_tab[16][F];        // grid mode: inv_coef by number of incidences (e = 4 x incidences)
+    int point[F];
 };
 
 // One check with NBK blocks (degree NBK + 2), one frame.  va = the values of its variables in ascending index
@@ -111,7 +118,27 @@ __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double 
     return part;
 }
 
-template <int F, int NB>
+// inv_coef, qp_admm.h:123-127 (A = (mu e - alpha)/2; inv = -1/(2A))
+__device__ __forceinline__ double inv_coef(double mu, double alpha, double e) {
+    const double A = __dmul_rn(__dadd_rn(__dmul_rn(mu, e), -alpha), 0.5);
+    return __ddiv_rn(-1.0, __dmul_rn(2.0, A));
+}
+
+// value of an auxiliary variable in iteration 0: z = yl = 0, so w = (0, 0, 0, mu (0 - 2)) in both of its blocks
+__device__ __forceinline__ double aux_start(double mu, double half_alpha, double inv_aux) {
+    const double w3 = __fma_rn(mu, __dadd_rn(0.0, -2.0), 0.0);
+    double B = __dadd_rn(half_alpha, -0.0);
+    B = __dadd_rn(B, -0.0);
+    B = __dadd_rn(B, 0.0);
+    B = __dadd_rn(B, w3);
+    B = __dadd_rn(B, 0.0);
+    B = __dadd_rn(B, -0.0);
+    B = __dadd_rn(B, -0.0);
+    B = __dadd_rn(B, w3);
+    return clip01_int(__dmul_rn(B, inv_aux));
+}
+
+template <int F, int NB, bool GRID>
 __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
@@ -132,10 +159,8 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
     double *red_gen = reinterpret_cast<double *>(sm + p.off_red);
 
     slots_init(S);
-    // inv_coef, qp_admm.h:123-127 (A = (mu e - alpha)/2; inv = -1/(2A))
     for (int r = tid; r < p.n_slots; r += nt) {
-        const double A = __dmul_rn(__dadd_rn(__dmul_rn(p.mu, (double) p.slot_e[r]), -p.alpha), 0.5);
-        reinterpret_cast<double *>(sm + p.off_inv)[r] = __ddiv_rn(-1.0, __dmul_rn(2.0, A));
+        reinterpret_cast<double *>(sm + p.off_inv)[r] = inv_coef(p.mu, p.alpha, (double) p.slot_e[r]);
         reinterpret_cast<uint32_t *>(sm + p.off_vw)[r] = p.var_words[r];
     }
     for (int a = tid; a < p.n_inc; a += nt) {
@@ -148,23 +173,10 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         L->c.q_next = L->c.q_end = 0;
         S->alive = F;
     }
-    const double half_alpha = __dmul_rn(p.alpha, 0.5), half_mu = __dmul_rn(p.mu, 0.5);
-    // auxiliary variables: e = 8 (two blocks x four rows)
-    const double inv_aux = __ddiv_rn(-1.0, __dmul_rn(2.0, __dmul_rn(__dadd_rn(__dmul_rn(p.mu, 8.0), -p.alpha), 0.5)));
-    // their value in iteration 0: z = yl = 0, so w = (0, 0, 0, mu (0 - 2)) in both blocks
-    double aux_init;
-    {
-        const double w3 = __fma_rn(p.mu, __dadd_rn(0.0, -2.0), 0.0);
-        double B = __dadd_rn(half_alpha, -0.0);
-        B = __dadd_rn(B, -0.0);
-        B = __dadd_rn(B, 0.0);
-        B = __dadd_rn(B, w3);
-        B = __dadd_rn(B, 0.0);
-        B = __dadd_rn(B, -0.0);
-        B = __dadd_rn(B, -0.0);
-        B = __dadd_rn(B, w3);
-        aux_init = clip01_int(__dmul_rn(B, inv_aux));
-    }
+    // penalty parameters of this lane's frame slot (grid mode: reloaded whenever a new work item enters the slot)
+    double mu = p.mu, half_mu = __dmul_rn(p.mu, 0.5), half_alpha = __dmul_rn(p.alpha, 0.5);
+    double inv_aux = inv_coef(p.mu, p.alpha, 8.0);     // auxiliary variables: e = 8 (two blocks x four rows)
+    double aux_init = aux_start(mu, half_alpha, inv_aux);
 
     // ---- this lane's check (static): degree, variable offsets, chunk offsets
     const bool has_chk = cr < p.n_chk;
@@ -193,6 +205,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
     const uint32_t vbuf = (uint32_t) p.n_slots * F * 8;
     const uint32_t a_qa = sbase + p.off_qa + f * 8;
     const uint32_t a_inv = sbase + p.off_inv, a_inc = sbase + p.off_inc, a_vw = sbase + p.off_vw;
+    const uint32_t a_invtab = smem_addr(&L->inv_tab[0][0]) + f * 8;
     __syncthreads();
 
     for (unsigned trip = 0;; ++trip) {
@@ -240,7 +253,8 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                     B = __dadd_rn(B, __hiloint2double(__double2hiint(a23.x) ^ (int) r.w, __double2loint(a23.x)));
                     B = __dadd_rn(B, a23.y);
                 }
-                sts_f64(a_vcur + slot * (F * 8), clip01_int(__dmul_rn(B, lds_f64(a_inv + slot * 8))));
+                const double ic = GRID ? lds_f64(a_invtab + (word & 15u) * (F * 8)) : lds_f64(a_inv + slot * 8);
+                sts_f64(a_vcur + slot * (F * 8), clip01_int(__dmul_rn(B, ic)));
             }
         }
         __syncthreads();
@@ -265,6 +279,15 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                 slot_finish<F>(io, S, q, 1, 1, valid, S->iter[q], cw,
                                [&](int i) { return vf[(size_t) p.var_slot[i] * F] > 0.5 ? 1 : 0; },
                                [&](int i) { return vf[(size_t) p.var_slot[i] * F]; });
+                if (GRID) {                          // the frame's counts go to its point's block
+                    __syncthreads();
+                    if (tid < LDPC_CNT_COUNT) {
+                        const unsigned long long cnt = S->cnt[tid];
+                        if (cnt) atomicAdd(&io.counters[(size_t) L->point[q] * LDPC_CNT_COUNT + tid], cnt);
+                        S->cnt[tid] = 0ull;
+                    }
+                    __syncthreads();
+                }
             }
             __syncthreads();
             if (warp == 0) {
@@ -283,8 +306,20 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                 }
                 if (want) {
                     const long long fr = rank < left ? next + rank : got + (rank - left);
-                    if (fr < io.frames) { S->frame[lane] = fr; S->iter[lane] = 0; S->hamming[lane] = 0; S->state[lane] = SLOT_NEW; }
-                    else S->state[lane] = SLOT_DEAD;
+                    if (fr < io.frames) {
+                        S->iter[lane] = 0; S->hamming[lane] = 0; S->state[lane] = SLOT_NEW;
+                        if (GRID) {
+                            const long long pt = fr / p.grid_frames;
+                            S->frame[lane] = fr - pt * p.grid_frames;
+                            L->point[lane] = (int) pt;
+                            L->alpha[lane] = p.grid_alpha[pt];
+                            L->mu[lane] = p.grid_mu[pt];
+                        } else {
+                            S->frame[lane] = fr;
+                        }
+                    } else {
+                        S->state[lane] = SLOT_DEAD;
+                    }
                 }
                 if (lane == 0) {
                     if (need > left) { L->c.q_next = got + (need - left); L->c.q_end = got + amt; }
@@ -305,10 +340,14 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
             if (S->alive == 0) break;
             const unsigned fresh = L->c.fresh;
             if (fresh) {
+                if (GRID && tid < 16 * F) {          // inv_coef of the slot's parameters by number of incidences
+                    const int q = tid % F, cnt = tid / F;
+                    if ((fresh >> q) & 1u) L->inv_tab[cnt][q] = inv_coef(L->mu[q], L->alpha[q], 4.0 * cnt);
+                }
                 // z = yl = 0 (qp_admm.h:120-121): w = mu (0 - b) -- the first variable phase of the frame reads it
-                const double w3 = __fma_rn(p.mu, __dadd_rn(0.0, -2.0), 0.0);
                 for (int i = tid; i < p.n_chunks * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) {
+                        const double w3 = __fma_rn(GRID ? L->mu[i % F] : p.mu, __dadd_rn(0.0, -2.0), 0.0);
                         sts_f64x2(sbase + i * 16, 0.0, 0.0);
                         sts_f64x2(sbase + p.off_w23 + i * 16, 0.0, w3);
                     }
@@ -316,7 +355,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                 // it goes to the buffer a frame that finishes at once is published from
                 slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int q, double l) {
                     const int r = p.var_slot[i];
-                    qa_gen[r * F + q] = __dadd_rn(l, half_alpha);
+                    qa_gen[r * F + q] = __dadd_rn(l, __dmul_rn(GRID ? L->alpha[q] : p.alpha, 0.5));
                     vcur_gen[r * F + q] = l > 0.0 ? 1.0 : 0.0;
                 });
             }
@@ -327,6 +366,13 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         const unsigned run = live & ~done;          // had a variable phase this trip and are not finished
         double part = 0.0;
         if ((fresh >> f) & 1u) {                    // a new frame moved into this lane's slot: z = yl = 0
+            if (GRID) {
+                mu = L->mu[f];
+                half_mu = __dmul_rn(mu, 0.5);
+                half_alpha = __dmul_rn(L->alpha[f], 0.5);
+                inv_aux = inv_coef(mu, L->alpha[f], 8.0);
+                aux_init = aux_start(mu, half_alpha, inv_aux);
+            }
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
                 yl[k][0] = yl[k][1] = yl[k][2] = yl[k][3] = 0.0;
@@ -340,7 +386,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
 #define LDPC_CHK_CASE(K)                                                                                          \
     case K:                                                                                                       \
         if (NB >= K)                                                                                              \
-            part = chk_update<(NB >= K ? K : 1), NB>(va, yl, aux, a_w01, p.off_w23, plane_off, p.mu, half_mu,     \
+            part = chk_update<(NB >= K ? K : 1), NB>(va, yl, aux, a_w01, p.off_w23, plane_off, mu, half_mu,       \
                                                      half_alpha, inv_aux);                                        \
         break;
             switch (nb) {
@@ -495,17 +541,33 @@ static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F,
 
 using ChkKernel = void (*)(const AdmmChkParams);
 
-template <int F>
+template <int F, bool GRID>
 static ChkKernel chk_kernel_for(int nb) {
-    if (nb <= 2) return qpadmm_chk_kernel<F, 2>;
-    if (nb <= 4) return qpadmm_chk_kernel<F, 4>;
-    if (nb == 5) return qpadmm_chk_kernel<F, 5>;
-    return qpadmm_chk_kernel<F, 6>;
+    if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID>;
+    if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID>;
+    if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID>;
+    return qpadmm_chk_kernel<F, 6, GRID>;
+}
+
+static ChkKernel chk_kernel_for(int F, int nb, bool grid) {
+    if (grid) return F == 4 ? chk_kernel_for<4, true>(nb) : (F == 2 ? chk_kernel_for<2, true>(nb) : chk_kernel_for<1, true>(nb));
+    return F == 4 ? chk_kernel_for<4, false>(nb) : (F == 2 ? chk_kernel_for<2, false>(nb) : chk_kernel_for<1, false>(nb));
+}
+
+// smallest 4 x column degree: DecodeQPADMM answers {zeros, false} when e_min * mu <= alpha (qp_admm.h:108-114)
+int qpadmm_chk_e_min(const ldpc_code *c) {
+    const AdmmChkTables *t = nullptr;
+    if (get_chk_tables(c, 1, &t) || !t->supported) return -1;
+    return t->e_min;
 }
 
 int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
-                      int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
+                      int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream,
+                      const double *grid_alpha, const double *grid_mu, int64_t grid_points) {
     if (frames <= 0) return LDPC_OK;
+    const bool grid = grid_points > 0;
+    const int64_t frames_per_point = frames;
+    if (grid) frames *= grid_points;             // work items of the queue
     // frames per CTA: one lane per (check, frame), at most 640 lanes.  Two CTAs of two frames per SM beat one CTA
     // of four (profiles/r01_admm_chk_sweep.txt): their barriers and their FP64-bound / latency-bound phases overlap.
     int F = 2;
@@ -524,32 +586,33 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
         if (c->m * F <= 640 && chk_smem_layout(c, *t, F, exp_mode, nullptr) <= 227 * 1024) break;
         if (F == 1) return LDPC_E_UNSUPPORTED;
     }
-    if ((double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
+    if (!grid && (double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
     AdmmChkParams p;
     KernelIO &io = p.io;
     io.y = fio.y; io.bits = fio.bits; io.ok = fio.ok; io.iters = fio.iters; io.soft = fio.soft;
     io.experiment = fio.experiment; io.cw_source = fio.cw_source; io.seed = fio.seed;
     io.frame_begin = fio.frame_begin; io.words = fio.words; io.n_words = fio.n_words;
     io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
-    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
+    io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);     // grid mode: frames = work items
     io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
     p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_slot = t->var_rank;
     p.slot_e = t->var_e;
     for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
     p.n_chk = c->m; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
     p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
+    p.grid_alpha = grid_alpha; p.grid_mu = grid_mu; p.grid_frames = frames_per_point;
     const int threads = chk_threads(c, F);
     const size_t smem = chk_smem_layout(c, *t, F, exp_mode, &p);
-    ChkKernel fn = F == 4 ? chk_kernel_for<4>(t->max_nb) : (F == 2 ? chk_kernel_for<2>(t->max_nb) : chk_kernel_for<1>(t->max_nb));
+    ChkKernel fn = chk_kernel_for(F, t->max_nb, grid);
     LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     if (per_sm < 1) return LDPC_E_UNSUPPORTED;
     const long long want = (frames + F - 1) / F;
-    const long long grid = std::min<long long>((long long) per_sm * sms, want);
-    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * 4 * F) * F));
-    fn<<<(unsigned) grid, threads, smem, stream>>>(p);
+    const long long ctas = std::min<long long>((long long) per_sm * sms, want);
+    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (ctas * 4 * F) * F));
+    fn<<<(unsigned) ctas, threads, smem, stream>>>(p);
     LDPC_CUDA(cudaGetLastError());
     return LDPC_OK;
 }

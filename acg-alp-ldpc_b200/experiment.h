@@ -133,6 +133,37 @@ inline ExperimentResult gpu_experiment(const GpuDecoder &decoder, const vector<T
     return total;
 }
 
+// The (alpha, mu) double loop of qpadmm_params.cpp:51-67 in one launch per GPU: the parameter pairs are
+// dealt to the visible GPUs, each GPU evaluates its pairs on all frames (ldpc_qpadmm_grid_run).  Returns the
+// result of every pair, in input order.
+inline vector<ExperimentResult> gpu_qpadmm_grid(const vector<double> &alphas, const vector<double> &mus, int max_iter,
+                                                double eps_stop, const vector<TCodeword> &codewords, const TMatrix &H,
+                                                double snr) {
+    const size_t points = alphas.size(), frames = codewords.size(), n = H[0].size();
+    vector<uint8_t> words(frames * n);
+    for (size_t f = 0; f < frames; ++f)
+        for (size_t i = 0; i < n; ++i) words[f * n + i] = codewords[f][i];
+    const int gpus = max(1, min<int>(visible_gpus(), (int) max<size_t>(points, 1)));
+    const uint64_t seed = experiment_seed();
+    vector<uint64_t> cnt(points * LDPC_CNT_COUNT, 0);
+    vector<double> secs(gpus, 0.0);
+    vector<thread> workers;
+    for (int g = 0; g < gpus; ++g)
+        workers.emplace_back([&, g] {
+            const size_t begin = points * g / gpus, end = points * (g + 1) / gpus;
+            if (begin == end) return;
+            ldpc_code_t *code = CodeCache::instance().get(H, g);
+            if (ldpc_qpadmm_grid_run(code, (int32_t) (end - begin), alphas.data() + begin, mus.data() + begin, max_iter,
+                                     eps_stop, snr, seed, 0, frames, LDPC_CW_TABLE, words.data(), frames,
+                                     cnt.data() + begin * LDPC_CNT_COUNT, &secs[g]) != LDPC_OK)
+                die("ldpc_qpadmm_grid_run");
+        });
+    for (thread &w : workers) w.join();
+    vector<ExperimentResult> out;
+    for (size_t i = 0; i < points; ++i) out.push_back(from_counters(cnt.data() + i * LDPC_CNT_COUNT, 0.0));
+    return out;
+}
+
 // The reference's exp() loop for arbitrary decoders, without its races: the frame
 // index comes from an atomic, and the noise generator is seeded with the 1-based
 // index of the frame it belongs to (what experiment.h:90-97 yields at one thread).

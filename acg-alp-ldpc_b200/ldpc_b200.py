@@ -69,6 +69,7 @@ def lib():
     L.ldpc_generator_codewords.argtypes = [vp, u64, u64, i64, vp]
     L.ldpc_experiment_run.argtypes = [vp, C.POINTER(AlgoCfg), dbl, u64, u64, u64, i32, vp, u64, vp,
                                       C.POINTER(dbl)]
+    L.ldpc_qpadmm_grid_run.argtypes = [vp, i32, vp, vp, i32, dbl, dbl, u64, u64, u64, i32, vp, u64, vp, C.POINTER(dbl)]
     L.ldpc_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.ldpc_host_free.argtypes = [vp]
     L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
@@ -209,6 +210,21 @@ class Code:
         res = dict(zip(CNT_NAMES, (int(x) for x in cnt)))
         res["gpu_seconds"] = secs.value
         return res
+
+
+    def qpadmm_grid(self, alphas, mus, snr, max_iter, eps_stop, seed, frame_begin, frame_count, source=CW_ZERO,
+                    words=None):
+        """qpadmm_params.cpp:51-67 in one launch -> (list of counter dicts in the order of alphas/mus, gpu seconds)"""
+        a = np.ascontiguousarray(alphas, np.float64)
+        m = np.ascontiguousarray(mus, np.float64)
+        assert a.shape == m.shape and a.ndim == 1
+        cnt = np.zeros((a.size, len(CNT_NAMES)), np.uint64)
+        secs = C.c_double()
+        w = None if words is None else np.ascontiguousarray(words, np.uint8)
+        _check(lib().ldpc_qpadmm_grid_run(self._h, a.size, a.ctypes.data, m.ctypes.data, max_iter, eps_stop, snr, seed,
+                                          frame_begin, frame_count, source, _ptr(w), 0 if w is None else w.shape[0],
+                                          cnt.ctypes.data, C.byref(secs)))
+        return [dict(zip(CNT_NAMES, (int(x) for x in row))) for row in cnt], secs.value
 
 
 class BeliefPropagationDecoder:

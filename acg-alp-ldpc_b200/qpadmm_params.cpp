@@ -46,20 +46,29 @@ int main() {
     cerr << "n=" << H[0].size() << " k=" << H.size() << endl;
 
     const double alpha_l = 0, alpha_r = 3.0, mu_l = 0, mu_r = 3.0, snr = -3.0;
-    double best_fer = 2.0, best_alpha = -1, best_mu = -1;
+    // all pairs of the grid in the reference's scan order (alpha outer, mu inner), evaluated in one launch per GPU
+    // (LDPC_GRID_BATCHED=0: one launch per pair, the reference's structure)
+    vector<double> alphas, mus;
     for (int ai = 0; ai < grid; ++ai)
         for (int mi = 0; mi < grid; ++mi) {
-            const double alpha = linear_function(alpha_l, alpha_r, grid, ai);
-            const double mu = linear_function(mu_l, mu_r, grid, mi);
-            const double fer = estimate_qpadmm(H, codewords, snr, alpha, mu);
-            cerr << "alpha=" << alpha << ", mu=" << mu << ": fer=" << fer << endl;
-            if (fer < best_fer) {
-                best_fer = fer;
-                best_alpha = alpha;
-                best_mu = mu;
-                cout << "new best fer found: " << fer << "| alpha=" << alpha << ", mu=" << mu << endl;
-            }
+            alphas.push_back(linear_function(alpha_l, alpha_r, grid, ai));
+            mus.push_back(linear_function(mu_l, mu_r, grid, mi));
         }
+    const bool batched = !(getenv("LDPC_GRID_BATCHED") && atoi(getenv("LDPC_GRID_BATCHED")) == 0);
+    vector<ExperimentResult> results;
+    if (batched) results = ldpc_host::gpu_qpadmm_grid(alphas, mus, 1000, 1e-5, codewords, H, snr);
+    double best_fer = 2.0, best_alpha = -1, best_mu = -1;
+    for (size_t i = 0; i < alphas.size(); ++i) {
+        const double alpha = alphas[i], mu = mus[i];
+        const double fer = batched ? results[i].FER() : estimate_qpadmm(H, codewords, snr, alpha, mu);
+        cerr << "alpha=" << alpha << ", mu=" << mu << ": fer=" << fer << endl;
+        if (fer < best_fer) {
+            best_fer = fer;
+            best_alpha = alpha;
+            best_mu = mu;
+            cout << "new best fer found: " << fer << "| alpha=" << alpha << ", mu=" << mu << endl;
+        }
+    }
 
     cout << "Best parameters:" << endl;
     cout << "alpha=" << best_alpha << endl;

@@ -166,6 +166,18 @@ int ldpc_experiment_run(const ldpc_code_t *code, const ldpc_algo_cfg_t *cfg, dou
                         const uint8_t *words, uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT],
                         double *gpu_seconds);
 
+/* ---- (alpha, mu) grid search: the double loop of qpadmm_params.cpp:51-67, whose body (estimate_qpadmm,
+ * :16-30) is multithread_experiment() with QPADMMDecoder(alpha, mu, max_iter, eps_stop).  ONE launch evaluates
+ * all `points` parameter pairs on the SAME frames [frame_begin, frame_begin + frame_count) (as the reference
+ * reuses its codewords and noise seeds for every pair): the work items (point, frame) share one queue, so the
+ * heavy-tailed iteration counts of one pair never idle the GPU.  counters: points x LDPC_CNT_COUNT (host), in
+ * the order of alpha[] / mu[].  Pairs with min(e) * mu <= alpha take the reference's {zeros, false} exit
+ * (qp_admm.h:108-114) as in ldpc_experiment_run. */
+int ldpc_qpadmm_grid_run(const ldpc_code_t *code, int32_t points, const double *alpha, const double *mu,
+                         int32_t max_iter, double eps_stop, double snr, uint64_t seed, uint64_t frame_begin,
+                         uint64_t frame_count, int32_t codeword_source, const uint8_t *words, uint64_t n_words,
+                         uint64_t *counters, double *gpu_seconds);
+
 /* ---- pinned host buffers for the host-pointer entry points (optional: any
  * host memory works, pinned memory makes the copies asynchronous). */
 int ldpc_host_alloc(void **ptr, uint64_t bytes);

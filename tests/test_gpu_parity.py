@@ -331,3 +331,24 @@ def test_admm_layout_removes_bank_conflicts(codes):
         print(name, "replayed wavefronts per iteration: natural", info["admm_conflicts_natural"], "laid out",
               info["admm_conflicts_laid_out"])
         assert info["admm_conflicts_laid_out"] <= info["admm_conflicts_natural"]
+
+
+@pytest.mark.gpu
+def test_qpadmm_grid_equals_point_by_point(codes, oracle):
+    """qpadmm_params.cpp:51-67 batched into one launch: every (alpha, mu) pair gets exactly the counters of its own
+    ldpc_experiment_run (same frames for every pair), including infeasible pairs (min(e) * mu <= alpha)"""
+    L = _lib(codes)
+    H, code, csr = codes["optimalH"]
+    m, n = H.shape
+    alphas = np.array([0.0, 1.2, 1.95, 3.0, 0.3, 2.25, 1.5], np.float64)
+    mus = np.array([0.5, 0.55, 0.5, 0.7, 0.0, 3.0, 0.4], np.float64)    # pairs 3 and 4 are infeasible (e_min = 4)
+    frames, snr, iters, eps = 257, -3.0, 300, 1e-5
+    grid, secs = code.qpadmm_grid(alphas, mus, snr, iters, eps, SEED, 11, frames)
+    assert secs > 0
+    for a, mu_, got in zip(alphas, mus, grid):
+        want = code.experiment(L.QPADMMDecoder(a, mu_, iters, eps), snr, SEED, 11, frames)
+        for k in got:
+            assert got[k] == want[k], (a, mu_, k, got[k], want[k])
+    # and one pair against the CPU oracle's replay
+    want = oracle.experiment("qpadmm", csr, m, n, snr, iters, SEED, 11, frames, alpha=1.2, mu=0.55, eps_stop=eps)
+    assert all(grid[1][k] == want[k] for k in want)
