@@ -511,12 +511,13 @@ static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, int64_t 
     return LDPC_OK;
 }
 
-// register budget by CTA size: 128 / 85 registers per thread
+// register budget by CTA size: 128 / 102 / 85 registers per thread
 template <int F>
 static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, int64_t frames, cudaStream_t stream) {
-    int maxt = threads <= 512 ? 512 : 768;
-    if (const char *force = getenv("LDPC_BP_MAXT")) maxt = atoi(force) > 512 ? 768 : 512;
-    if (maxt == 512 && threads <= 512) return launch_lr_ft<F, 512>(p, c, threads, frames, stream);
+    int maxt = threads <= 512 ? 512 : (threads <= 640 ? 640 : 768);
+    if (const char *force = getenv("LDPC_BP_MAXT")) maxt = std::max(maxt, atoi(force));
+    if (maxt <= 512) return launch_lr_ft<F, 512>(p, c, threads, frames, stream);
+    if (maxt <= 640) return launch_lr_ft<F, 640>(p, c, threads, frames, stream);
     return launch_lr_ft<F, 768>(p, c, threads, frames, stream);
 }
 

@@ -63,7 +63,7 @@ struct AdmmChkParams {
 struct ChkCtl {
     unsigned live;                // slots holding a frame
     unsigned ran;                 // slots that took part in the last check phase
-    unsigned done;                // slots whose frame is finished (set by warp 0 during the variable phase)
+    unsigned done[2];             // by trip parity: slots whose frame is finished (set by warps 0..F-1 during the variable phase)
     unsigned fresh;
     long long q_next, q_end;
 };
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         reinterpret_cast<uint4 *>(sm + p.off_inc)[a] = rec;
     }
     if (tid == 0) {
-        L->c.live = L->c.ran = L->c.done = L->c.fresh = 0u;
+        L->c.live = L->c.ran = L->c.done[0] = L->c.done[1] = L->c.fresh = 0u;
         L->c.q_next = L->c.q_end = 0;
         S->alive = F;
     }
@@ -214,30 +214,22 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         const double *vprev_gen = v_gen + (size_t) ((trip & 1) ^ 1) * p.n_slots * F;
         const unsigned live = L->c.live, ran = L->c.ran;
 
-        // ---- warp 0: stop test of the previous check phase (qp_admm.h:161-163) / out of iterations
-        if (warp == 0) {
-            const int ff = lane / LPF, j = lane % LPF;
-            double sum2 = 0.0;
-            if ((ran >> ff) & 1u)
-                for (int w = j; w < nwarps; w += LPF) sum2 += red_gen[ff * 32 + w];
+        // ---- warp q < F: stop test of slot q after the previous check phase (qp_admm.h:161-163) / out of iterations;
+        // lane j adds the partial of warp j, then a shuffle tree
+        if (warp < F) {
+            const int q = warp;
+            double sum2 = (((ran >> q) & 1u) && lane < nwarps) ? red_gen[q * 32 + lane] : 0.0;
 #pragma unroll
-            for (int off = LPF / 2; off >= 1; off >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
-            bool fin = false;
-            if (j == 0 && ((live >> ff) & 1u)) {
-                const int it = S->iter[ff];
-                fin = (((ran >> ff) & 1u) && sum2 < p.eps_stop) || it >= p.max_iter;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, fin);
-            unsigned done = 0;
-#pragma unroll
-            for (int q = 0; q < F; ++q) done |= ((bal >> (q * LPF)) & 1u) << q;
-            if (lane == 0) {
-                L->c.done = done;
-                L->c.fresh = 0u;      // everybody read it before the last barrier; the refill below sets it again
+            for (int off = 16; off >= 1; off >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
+            if (lane == 0 && ((live >> q) & 1u)) {
+                const bool fin = (((ran >> q) & 1u) && sum2 < p.eps_stop) || S->iter[q] >= p.max_iter;
+                if (fin) atomicOr(&L->c.done[trip & 1], 1u << q);
             }
         }
+        if (tid == 0) L->c.fresh = 0u;    // everybody read it before the last barrier; the refill below sets it again
 
         // ---- variable phase, qp_admm.h:132-142: this lane's column of variable slots
+        // (prefetching the next incidence's records and row terms costs more in registers than it hides: 153 vs 141 ms)
         if ((live >> f) & 1u) {
             for (int slot = cr; slot < p.n_slots; slot += cpt) {
                 const uint32_t word = lds_u32(a_vw + slot * 4);
@@ -260,7 +252,8 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         __syncthreads();
 
         // ---- publish finished frames (from the previous buffer), refill their slots
-        const unsigned done = L->c.done;
+        const unsigned done = L->c.done[trip & 1];
+        if (tid == 0) L->c.done[(trip & 1) ^ 1] = 0u;      // the buffer of the next trip; last read a trip ago
         if (done || trip == 0) {
             for (int q = 0; q < F; ++q) {
                 if (!((done >> q) & 1u)) continue;
