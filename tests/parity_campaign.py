@@ -84,8 +84,18 @@ def main():
         bad = np.flatnonzero((gb != ob).any(1) | (gok != ook) | (git != oit))
         conv = (gok == 1) & (ook == 1)
         if algo == "bp":
-            rel = np.abs(gsoft[conv] - osoft[conv]) / np.maximum(np.abs(osoft[conv]), 1e-300)
-            soft_note = "max rel posterior-LLR error over converged frames %.3g" % (rel.max() if rel.size else 0.0)
+            # The reference's phi form is itself inaccurate at large magnitudes: tanh(x/2) = 1 - 2 exp(-x) carries a
+            # relative error of 2^-64 exp(x) / 2 in fp80 (1e-4 at |LLR| ~ 35) and saturates to infinity from ~45.7 on, so
+            # the 1e-4 bar is checked where the reference can deliver it and the rest is counted.
+            g, o = gsoft[conv], osoft[conv]
+            fin = np.isfinite(o) & (np.abs(o) <= 30.0)
+            rel = np.abs(g[fin] - o[fin]) / np.maximum(np.abs(o[fin]), 1e-300)
+            big = ~fin & np.isfinite(o)
+            rel_big = np.abs(g[big] - o[big]) / np.abs(o[big]) if big.any() else np.zeros(0)
+            soft_note = ("posterior LLR: max rel error %.3g over %d values with |LLR| <= 30; %.3g over %d values with 30 < |LLR| "
+                         "< inf; %d values where the reference saturated to inf" % (
+                             rel.max() if rel.size else 0.0, int(fin.sum()), rel_big.max() if rel_big.size else 0.0,
+                             int(big.sum()), int((~np.isfinite(o)).sum())))
         else:
             soft_note = "v bit-identical on %d of %d frames" % (int((gsoft == osoft).all(1).sum()), frames)
         lines.append("%-7s %-13s snr %5.1f  frames %6d  mismatching %d (%.4f %%)  converged gpu/cpu %d/%d  mean iters %.1f  %s"
