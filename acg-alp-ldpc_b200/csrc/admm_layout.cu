@@ -234,14 +234,14 @@ int compile_admm(ldpc_code *c) {
     for (int r = 0; r < nb; ++r) L.rank_b[L.at_b[r]] = r;
     c->admm_conflicts_before = L.replayed_wavefronts();
     int moves = 40 * (nv + nb);   // ~40 ms for the 160 x 280 codes; H changes per proposal in optimize_H.cpp
-    // Codes the check-centric kernel decodes (qpadmm_chk_kernel.cu: every check of degree 3..8) use this kernel only for
+    // Codes the check-centric kernel decodes (qpadmm_chk_kernel.cu: every check of degree <= 12) use this kernel only for
     // the zero-iteration exit of infeasible (alpha, mu): the natural order will do
     bool chk_kernel = true;
     for (int r = 0; r < m && chk_kernel; ++r) {
         const int d = c->row_ptr[r + 1] - c->row_ptr[r];
-        chk_kernel = d >= 3 && d <= 8;
+        chk_kernel = d <= 12;
     }
-    for (int v = 0; v < n && chk_kernel; ++v) chk_kernel = !L.var_blocks[v].empty() && L.var_blocks[v].size() <= 15;
+    for (int v = 0; v < n && chk_kernel; ++v) chk_kernel = L.var_blocks[v].size() <= 15;
     if (chk_kernel) moves = 0;
     if (const char *s = getenv("LDPC_ADMM_LAYOUT_MOVES")) moves = atoi(s);
     if (moves > 0) {

@@ -78,8 +78,9 @@ struct AdmmChkTables {
     uint32_t *chk_tab = nullptr, *var_words = nullptr;
     uint4 *var_inc = nullptr;
     uint16_t *var_rank = nullptr, *var_e = nullptr;
-    uint32_t plane_base[6] = {0, 0, 0, 0, 0, 0};
-    int n_chunks = 0, n_inc = 0, n_slots = 0, tab_stride = 0, max_nb = 0, e_min = 0;
+    uint32_t plane_base[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int special_lo = 0, special_hi = 0;
+    int n_chk = 0, n_chunks = 0, n_inc = 0, n_slots = 0, tab_stride = 0, max_nb = 0, e_min = 0;
 };
 
 struct DeviceTables {

@@ -1,5 +1,6 @@
 // QP-ADMM decoding, check-centric kernel (sm_100a) -- DecodeQPADMM, algo/qp_admm.h:104-178, for codes
-// whose checks all have degree 3..8 (every code of BASELINE.json).  qpadmm_kernel.cu serves the rest.
+// whose checks have degree <= 12 and whose variables have at most 15 edges (every code of BASELINE.json and the
+// proposals of optimize_H.cpp, including their degree-0/1/2 checks).  qpadmm_kernel.cu serves the rest.
 //
 // ConstructADMMProblem (qp_admm.h:59-92) splits a check of degree d into a chain of d - 2 three-variable
 // blocks that are linked by d - 3 auxiliary variables, and every auxiliary variable belongs to exactly two
@@ -38,17 +39,19 @@
 
 namespace ldpc {
 
-constexpr int CHK_MAX_NB = 6;     // blocks per check (degree <= 8)
+constexpr int CHK_MAX_NB = 10;    // blocks per check (degree <= 12)
+constexpr uint32_t CHK_EMPTY_SLOT = 0xffffffffu;
 
 struct AdmmChkParams {
     KernelIO io;
     const uint32_t *chk_tab;      // per check rank: tab_stride words: degree, then the STORAGE SLOTS of its variables (ascending variable index)
-    const uint32_t *var_words;    // per variable slot: (offset of its incidence records) << 4 | incidences; 0 = empty slot
+    const uint32_t *var_words;    // per variable slot: (offset of its incidence records) << 10 | e << 4 | incidences, or CHK_EMPTY_SLOT
     const uint4 *var_inc;         // incidence records {chunk index, flip mask w0, flip mask w1, flip mask w2}, row order
     const uint16_t *var_slot;     // variable index -> storage slot
     const uint16_t *slot_e;       // per slot: sum of squared coefficients of the variable's column (qp_admm.h:94-99)
     uint32_t plane_base[CHK_MAX_NB];   // chunk index of check rank 0's k-th block
     int n_chk, n_slots, n_chunks, n_inc, tab_stride;
+    int special_lo, special_hi;   // chunks [lo, hi) belong to one- and two-variable checks (no row with b = 2)
     // byte offsets of the arrays in dynamic shared memory
     uint32_t off_w23, off_v, off_qa, off_inv, off_red, off_inc, off_vw, off_cw, off_ctl;
     int max_iter;
@@ -73,7 +76,7 @@ struct ChkShared {
     SlotBlock<F> S;
     ChkCtl c;
     double alpha[F], mu[F];       // grid mode: parameters of the slot's work item
-    double inv_tab[16][F];        // grid mode: inv_coef by number of incidences (e = 4 x incidences)
+    double inv_tab[64][F];        // grid mode: inv_coef by e (sum of squared coefficients of the column, <= 60)
     int point[F];
 };
 
@@ -138,8 +141,24 @@ __device__ __forceinline__ double aux_start(double mu, double half_alpha, double
     return clip01_int(__dmul_rn(B, inv_aux));
 }
 
+// A check of degree 1 or 2 (qp_admm.h:70-83): ROWS = degree inequality rows with b = 0 and no auxiliary variable;
+// the missing rows of its chunk stay zero, so the variable phase needs no special case.
+template <int ROWS>
+__device__ __forceinline__ double chk_special(double v0, double v1, double &yl0, double &yl1, uint32_t a_w01,
+                                              uint32_t off_w23, uint32_t plane_off0, double mu, double half_mu) {
+    double part = 0.0;
+    // r = b - A v in ascending variable order: row 0 = (+1, -1), row 1 = (-1, +1)
+    const double r0 = ROWS == 2 ? __dadd_rn(-v0, v1) : -v0;
+    const double w0 = row_update_fp<false>(r0, yl0, part, mu, half_mu);
+    double w1 = 0.0;
+    if (ROWS == 2) w1 = row_update_fp<false>(__dadd_rn(v0, -v1), yl1, part, mu, half_mu);
+    sts_f64x2(a_w01 + plane_off0, w0, w1);
+    sts_f64x2(a_w01 + off_w23 + plane_off0, 0.0, 0.0);
+    return part;
+}
+
 template <int F, int NB, bool GRID>
-__global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
+__global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
     const int n = io.n;
@@ -180,7 +199,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
 
     // ---- this lane's check (static): degree, variable offsets, chunk offsets
     const bool has_chk = cr < p.n_chk;
-    int nb = 0;
+    int nb = -2;                                   // degree - 2: -1 / 0 = the one- and two-variable checks
     uint32_t voff[NB + 2], plane_off[NB];
 #pragma unroll
     for (int j = 0; j < NB + 2; ++j) voff[j] = 0;
@@ -233,8 +252,8 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
         if ((live >> f) & 1u) {
             for (int slot = cr; slot < p.n_slots; slot += cpt) {
                 const uint32_t word = lds_u32(a_vw + slot * 4);
-                if (word == 0u) continue;                               // empty slot
-                uint32_t rec = a_inc + (word >> 4) * 16;
+                if (word == CHK_EMPTY_SLOT) continue;
+                uint32_t rec = a_inc + (word >> 10) * 16;
                 const uint32_t rec_end = rec + (word & 15u) * 16;
                 double B = lds_f64(a_qa + slot * (F * 8));
                 for (; rec != rec_end; rec += 16) {
@@ -245,7 +264,7 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                     B = __dadd_rn(B, __hiloint2double(__double2hiint(a23.x) ^ (int) r.w, __double2loint(a23.x)));
                     B = __dadd_rn(B, a23.y);
                 }
-                const double ic = GRID ? lds_f64(a_invtab + (word & 15u) * (F * 8)) : lds_f64(a_inv + slot * 8);
+                const double ic = GRID ? lds_f64(a_invtab + ((word >> 4) & 63u) * (F * 8)) : lds_f64(a_inv + slot * 8);
                 sts_f64(a_vcur + slot * (F * 8), clip01_int(__dmul_rn(B, ic)));
             }
         }
@@ -333,14 +352,16 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
             if (S->alive == 0) break;
             const unsigned fresh = L->c.fresh;
             if (fresh) {
-                if (GRID && tid < 16 * F) {          // inv_coef of the slot's parameters by number of incidences
-                    const int q = tid % F, cnt = tid / F;
-                    if ((fresh >> q) & 1u) L->inv_tab[cnt][q] = inv_coef(L->mu[q], L->alpha[q], 4.0 * cnt);
+                if (GRID && tid < 64 * F) {          // inv_coef of the slot's parameters by e
+                    const int q = tid % F, e = tid / F;
+                    if ((fresh >> q) & 1u) L->inv_tab[e][q] = inv_coef(L->mu[q], L->alpha[q], (double) e);
                 }
                 // z = yl = 0 (qp_admm.h:120-121): w = mu (0 - b) -- the first variable phase of the frame reads it
                 for (int i = tid; i < p.n_chunks * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) {
-                        const double w3 = __fma_rn(GRID ? L->mu[i % F] : p.mu, __dadd_rn(0.0, -2.0), 0.0);
+                        const int chunk = i / F;
+                        const double b3 = (chunk >= p.special_lo && chunk < p.special_hi) ? 0.0 : 2.0;
+                        const double w3 = __fma_rn(GRID ? L->mu[i % F] : p.mu, __dadd_rn(0.0, -b3), 0.0);
                         sts_f64x2(sbase + i * 16, 0.0, 0.0);
                         sts_f64x2(sbase + p.off_w23 + i * 16, 0.0, w3);
                     }
@@ -383,7 +404,10 @@ __global__ void __launch_bounds__(640, 1) qpadmm_chk_kernel(const AdmmChkParams 
                                                      half_alpha, inv_aux);                                        \
         break;
             switch (nb) {
+                case -1: part = chk_special<1>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
+                case 0: part = chk_special<2>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
                 LDPC_CHK_CASE(1) LDPC_CHK_CASE(2) LDPC_CHK_CASE(3) LDPC_CHK_CASE(4) LDPC_CHK_CASE(5) LDPC_CHK_CASE(6)
+                LDPC_CHK_CASE(7) LDPC_CHK_CASE(8) LDPC_CHK_CASE(9) LDPC_CHK_CASE(10)
                 default: break;
             }
 #undef LDPC_CHK_CASE
@@ -410,34 +434,47 @@ static int upload_chk(T **dst, const std::vector<T> &src) {
     return LDPC_OK;
 }
 
-static int chk_threads(const ldpc_code *c, int F) { return (c->m * F + 31) / 32 * 32; }
+static int live_checks(const ldpc_code *c) {
+    int k = 0;
+    for (int r = 0; r < c->m; ++r) k += c->row_ptr[r + 1] > c->row_ptr[r];
+    return k;
+}
+
+static int chk_threads(const ldpc_code *c, int F) { return (std::max(1, live_checks(c)) * F + 31) / 32 * 32; }
 
 // Tables of the check-centric kernel for F frames per CTA (the variable slots depend on the CTA's column count);
-// `supported` = every check has degree 3..8 and every variable 1..15 edges.
+// `supported` = every check has degree <= 12 and every variable at most 15 edges.
 static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) {
     std::lock_guard<std::mutex> lock(c->sched_mu);
     AdmmChkTables &t = c->admm_chk[F == 4 ? 2 : (F == 2 ? 1 : 0)];
     if (!t.built) {
         t.built = true;
         t.supported = c->m > 0 && c->n < 65535;
+        int live_checks = 0;
         for (int r = 0; r < c->m && t.supported; ++r) {
             const int d = c->row_ptr[r + 1] - c->row_ptr[r];
-            if (d < 3 || d > CHK_MAX_NB + 2) t.supported = false;
+            if (d > CHK_MAX_NB + 2) t.supported = false;
+            live_checks += d > 0;
         }
         for (int v = 0; v < c->n && t.supported; ++v)
-            if (c->col_ptr[v + 1] == c->col_ptr[v] || c->col_ptr[v + 1] - c->col_ptr[v] > 15) t.supported = false;
+            if (c->col_ptr[v + 1] - c->col_ptr[v] > 15) t.supported = false;
+        if (live_checks == 0) t.supported = false;
         if (t.supported) {
-            const int m = c->m, n = c->n;
-            // checks by degree (descending, stable), variables by degree (descending, stable)
-            std::vector<int> chk(m), var(n), rank_of_chk(m);
-            for (int i = 0; i < m; ++i) chk[i] = i;
-            for (int i = 0; i < n; ++i) var[i] = i;
+            const int n = c->n;
+            // checks with at least one edge by degree (descending, stable; checks without edges have no rows,
+            // qp_admm.h:67-69), variables by degree (descending, stable)
             auto cdeg = [&](int r) { return c->row_ptr[r + 1] - c->row_ptr[r]; };
             auto vdeg = [&](int v) { return c->col_ptr[v + 1] - c->col_ptr[v]; };
+            std::vector<int> chk, var(n), rank_of_chk(c->m, -1);
+            for (int i = 0; i < c->m; ++i)
+                if (cdeg(i) > 0) chk.push_back(i);
+            const int m = (int) chk.size();
+            for (int i = 0; i < n; ++i) var[i] = i;
             std::stable_sort(chk.begin(), chk.end(), [&](int a, int b) { return cdeg(a) > cdeg(b); });
             std::stable_sort(var.begin(), var.end(), [&](int a, int b) { return vdeg(a) > vdeg(b); });
             for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
-            t.max_nb = cdeg(chk[0]) - 2;
+            t.n_chk = m;
+            t.max_nb = std::max(1, cdeg(chk[0]) - 2);
             // Variable slots: lane column c of the CTA updates the slots c, c + cols, c + 2 cols, ...  The variables
             // are dealt to the columns in boustrophedon order, heaviest first, so that every column gets about the
             // same number of incidences (the variable phase ends at a barrier) and neighbouring columns -- the lanes
@@ -457,10 +494,16 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
             for (int k = 0; k < CHK_MAX_NB; ++k) {
                 t.plane_base[k] = (uint32_t) base;
                 int cnt = 0;
-                for (int i = 0; i < m; ++i) cnt += cdeg(chk[i]) - 2 > k;
+                for (int i = 0; i < m; ++i) cnt += std::max(1, cdeg(chk[i]) - 2) > k;    // one- and two-variable checks: one chunk
                 base += (cnt + 1) & ~1;            // even bases: neighbouring checks write neighbouring rows
             }
             t.n_chunks = base;
+            {   // the one- and two-variable checks are the last ranks (degree descending): their chunks in plane 0
+                int m3 = 0;
+                for (int i = 0; i < m; ++i) m3 += cdeg(chk[i]) >= 3;
+                t.special_lo = (int) t.plane_base[0] + m3;
+                t.special_hi = (int) t.plane_base[0] + m;
+            }
             t.tab_stride = CHK_MAX_NB + 3;
             std::vector<uint32_t> tab((size_t) m * t.tab_stride, 0u);
             for (int i = 0; i < m; ++i) {
@@ -470,31 +513,45 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
                     tab[(size_t) i * t.tab_stride + 1 + j] = (uint32_t) slot_of_var[c->col_idx[e]];
             }
             // variable incidences in ascending row order = ascending check index (a variable is in one block per check)
-            std::vector<uint32_t> words(t.n_slots, 0u);
+            std::vector<uint32_t> words(t.n_slots, CHK_EMPTY_SLOT);
             std::vector<uint4> inc;
             std::vector<uint16_t> vslot(n), se(t.n_slots, 4);
-            int e_min = 1 << 30;
+            int e_min = 1000000000;                       // over ALL variables, as qp_admm.h:108-111
+            for (int r : chk)
+                if (cdeg(r) >= 4) e_min = std::min(e_min, 8);     // auxiliary variables: two blocks x four rows
             for (int sl = 0; sl < t.n_slots; ++sl) {
                 const int v = var_of_slot[sl];
                 if (v < 0) continue;
                 vslot[v] = (uint16_t) sl;
-                words[sl] = ((uint32_t) inc.size() << 4) | (uint32_t) vdeg(v);
-                se[sl] = (uint16_t) (4 * vdeg(v));
-                e_min = std::min(e_min, 4 * vdeg(v));
+                const uint32_t first = (uint32_t) inc.size();
+                int e = 0;
                 for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) {
-                    const int e = c->csc_edge[q];
-                    const int r = (int) (std::upper_bound(c->row_ptr.begin(), c->row_ptr.end(), e) - c->row_ptr.begin()) - 1;
-                    const int d = cdeg(r), j = e - c->row_ptr[r];
-                    const int k = j == 0 ? 0 : (j == d - 1 ? d - 3 : j - 1);
-                    const int slot = j == 0 ? 0 : (j == d - 1 ? 2 : 1);
+                    const int edge = c->csc_edge[q];
+                    const int r = (int) (std::upper_bound(c->row_ptr.begin(), c->row_ptr.end(), edge) - c->row_ptr.begin()) - 1;
+                    const int d = cdeg(r), j = edge - c->row_ptr[r];
                     uint4 rec;
-                    rec.x = t.plane_base[k] + (uint32_t) rank_of_chk[r];
-                    rec.y = slot == 0 ? 0u : 0x80000000u;
-                    rec.z = slot == 1 ? 0u : 0x80000000u;
-                    rec.w = slot == 2 ? 0u : 0x80000000u;
+                    if (d >= 3) {               // block and slot of the variable in the chain (qp_admm.h:84-91)
+                        const int k = j == 0 ? 0 : (j == d - 1 ? d - 3 : j - 1);
+                        const int slot = j == 0 ? 0 : (j == d - 1 ? 2 : 1);
+                        rec.x = t.plane_base[k] + (uint32_t) rank_of_chk[r];
+                        rec.y = slot == 0 ? 0u : 0x80000000u;
+                        rec.z = slot == 1 ? 0u : 0x80000000u;
+                        rec.w = slot == 2 ? 0u : 0x80000000u;
+                        e += 4;
+                    } else {                    // qp_admm.h:70-83: rows (+1) or (+1, -1) / (-1, +1); the chunk's other rows are zero
+                        rec.x = t.plane_base[0] + (uint32_t) rank_of_chk[r];
+                        rec.y = j == 0 ? 0u : 0x80000000u;
+                        rec.z = j == 1 ? 0u : 0x80000000u;
+                        rec.w = 0u;
+                        e += d;
+                    }
                     inc.push_back(rec);
                 }
+                words[sl] = (first << 10) | ((uint32_t) e << 4) | (uint32_t) vdeg(v);
+                se[sl] = (uint16_t) e;
+                e_min = std::min(e_min, e);
             }
+            if (inc.size() >= (1u << 22)) t.supported = false;
             t.n_inc = (int) inc.size();
             t.e_min = e_min;
             int st;
@@ -539,7 +596,9 @@ static ChkKernel chk_kernel_for(int nb) {
     if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID>;
     if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID>;
     if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID>;
-    return qpadmm_chk_kernel<F, 6, GRID>;
+    if (nb == 6) return qpadmm_chk_kernel<F, 6, GRID>;
+    if (nb <= 8) return qpadmm_chk_kernel<F, 8, GRID>;
+    return qpadmm_chk_kernel<F, 10, GRID>;
 }
 
 static ChkKernel chk_kernel_for(int F, int nb, bool grid) {
@@ -576,7 +635,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
         int st = get_chk_tables(c, F, &t);
         if (st) return st;
         if (!t->supported) return LDPC_E_UNSUPPORTED;
-        if (c->m * F <= 640 && chk_smem_layout(c, *t, F, exp_mode, nullptr) <= 227 * 1024) break;
+        if (chk_threads(c, F) <= (t->max_nb <= 6 ? 640 : 320) && chk_smem_layout(c, *t, F, exp_mode, nullptr) <= 227 * 1024) break;
         if (F == 1) return LDPC_E_UNSUPPORTED;
     }
     if (!grid && (double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
@@ -591,7 +650,8 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_slot = t->var_rank;
     p.slot_e = t->var_e;
     for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
-    p.n_chk = c->m; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
+    p.special_lo = t->special_lo; p.special_hi = t->special_hi;
+    p.n_chk = t->n_chk; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
     p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
     p.grid_alpha = grid_alpha; p.grid_mu = grid_mu; p.grid_frames = frames_per_point;
     const int threads = chk_threads(c, F);

@@ -45,11 +45,22 @@ TCodeword gen_random_codeword(const vector<TCodeword> &G, Gen &rnd) {
     return gf2::unpack(acc, G[0].size());
 }
 
+// n codewords (utils/channel.h:38-44); the rows of G are packed once, the generator is consumed exactly as by n
+// calls of gen_random_codeword (one draw per row, row order)
 template <typename Gen>
 vector<TCodeword> gen_random_codewords(const TMatrix &G, int n, Gen &rnd) {
+    assert(!G.empty());
+    vector<gf2::Packed> rows;
+    rows.reserve(G.size());
+    for (const TCodeword &row : G) rows.push_back(gf2::pack(row));
     vector<TCodeword> words;
     words.reserve(n);
-    while ((int) words.size() < n) words.push_back(gen_random_codeword(G, rnd));
+    while ((int) words.size() < n) {
+        gf2::Packed acc((G[0].size() + 63) / 64, 0);
+        for (const gf2::Packed &row : rows)
+            if (rnd() % 2 == 0) gf2::xor_into(acc, row);
+        words.push_back(gf2::unpack(acc, G[0].size()));
+    }
     return words;
 }
 
