@@ -40,6 +40,7 @@
 // variable pass from the sign bits it loads), barrier, frames that converged or ran out
 // of iterations are published and their slots refilled, variable pass, barrier.
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -55,6 +56,8 @@ struct BpLrParams {
     KernelIO io;
     const uint32_t *rec_v;      // variable records (words): [var * F * 8, slot_0 * F * 8, ..., slot_{d-1} * F * 8], padded to 4 words
     const uint32_t *steps;      // per warp: steps_per_warp words, variable pass then check pass, each list ends with 0
+    const uint16_t *var_store;  // variable index -> storage index of its L_ch / decision / posterior (rank order)
+    int pad_even;               // 1: the checks of an even-degree class are stored with stride degree + 1 (see host side)
     int rec_words;              // total words of rec_v
     int steps_per_warp, steps_c_off;
     int E;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         const uint32_t nx = *++q;                                                                           \
         const int deg = (int) (e >> 23);                                                                    \
         if (node_lane <= (int) ((e >> 18) & 31u))                                                           \
-            bad |= (unsigned) lr_chk_update<D, FB>(msg_p + (e & 0x3ffffu) + node_lane * deg * FB, deg, p.clamp_hi); \
+            bad |= (unsigned) lr_chk_update<D, FB>(msg_p + (e & 0x3ffffu) + node_lane * (deg | p.pad_even) * FB, deg, p.clamp_hi); \
         e = nx;                                                                                             \
     }
                 LDPC_CHK_STEPS(0, (e >> 23) > 8)
@@ -279,9 +282,9 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
                 const int ok = (okmask >> f) & 1u;
                 const uint8_t *df = dec + f;
                 const char *pf = post + f * 8;
-                slot_finish<F>(io, S, f, ok, ok, ok, S->iter[f], cw, [&](int i) { return (int) df[(size_t) i * F]; },
+                slot_finish<F>(io, S, f, ok, ok, ok, S->iter[f], cw, [&](int i) { return (int) df[(size_t) p.var_store[i] * F]; },
                                [&](int i) {
-                                   const double t = ld_f64(pf + (size_t) i * FB);
+                                   const double t = ld_f64(pf + (size_t) p.var_store[i] * FB);
                                    return log_pos(fmin(fmax(t, 1e-300), 1e300));
                                });
             }
@@ -331,9 +334,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
                 // L_ch = exp(llr), llr clamped to +-llr_cap; variables without edges keep decision / posterior of the channel
                 slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int f, double l) {
                     const double lc = exp_signed(fmin(fmax(l, -p.llr_cap), p.llr_cap));
-                    st_f64(lch + (size_t) i * FB + f * 8, lc);
-                    dec[(size_t) i * F + f] = (uint8_t) (lc <= 1.0);
-                    if (p.soft) st_f64(post + (size_t) i * FB + f * 8, lc);
+                    const size_t st = p.var_store[i];
+                    st_f64(lch + st * FB + f * 8, lc);
+                    dec[st * F + f] = (uint8_t) (lc <= 1.0);
+                    if (p.soft) st_f64(post + st * FB + f * 8, lc);
                 });
             }
         }
@@ -384,8 +388,8 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
 
 // ---------------------------------------------------------------- host side
 
-static size_t lr_smem_bytes(const ldpc_code *c, int F, bool soft, bool experiment, int rec_words, int step_words) {
-    return (size_t) F * 8 * ((size_t) c->E + (size_t) c->n * (soft ? 2 : 1)) + (size_t) F * c->n * (experiment ? 2 : 1) +
+static size_t lr_smem_bytes(const ldpc_code *c, int n_slots, int F, bool soft, bool experiment, int rec_words, int step_words) {
+    return (size_t) F * 8 * ((size_t) n_slots + (size_t) c->n * (soft ? 2 : 1)) + (size_t) F * c->n * (experiment ? 2 : 1) +
            (size_t) 4 * (rec_words + step_words) + 16 + sizeof(SlotBlock<32>) + 256;
 }
 
@@ -429,22 +433,174 @@ static int upload_vec(T **dst, const std::vector<T> &src) {
     return LDPC_OK;
 }
 
+// Balanced 2-colouring of the edges of the Tanner graph: every variable and every check gets as many edges of colour
+// 0 as of colour 1 (+-1 for odd degrees).  Euler partition: nodes of odd degree are joined to a dummy node of the
+// other side (the two dummies to each other if their degrees are odd), every node then has even degree, the edge set
+// splits into closed trails, and a trail of a bipartite graph has even length, so colouring it alternately gives every
+// node visit one edge of each colour.
+static void lr_balanced_colouring(const ldpc_code *c, std::vector<int> &colour) {
+    const int n = c->n, m = c->m, E = c->E;
+    const int dummy_var = n + m, dummy_chk = n + m + 1, nodes = n + m + 2;
+    struct Ed { int a, b; };
+    std::vector<Ed> edges;
+    for (int r = 0; r < m; ++r)
+        for (int e = c->row_ptr[r]; e < c->row_ptr[r + 1]; ++e) edges.push_back(Ed{c->col_idx[e], n + r});
+    int odd = 0;
+    for (int v = 0; v < n; ++v)
+        if ((c->col_ptr[v + 1] - c->col_ptr[v]) & 1) { edges.push_back(Ed{v, dummy_chk}); ++odd; }
+    for (int r = 0; r < m; ++r)
+        if ((c->row_ptr[r + 1] - c->row_ptr[r]) & 1) edges.push_back(Ed{dummy_var, n + r});
+    if (odd & 1) edges.push_back(Ed{dummy_var, dummy_chk});
+    std::vector<std::vector<int>> adj(nodes);
+    for (int e = 0; e < (int) edges.size(); ++e) { adj[edges[e].a].push_back(e); adj[edges[e].b].push_back(e); }
+    std::vector<char> used(edges.size(), 0);
+    std::vector<size_t> next(nodes, 0);
+    std::vector<int> col(edges.size(), 0);
+    for (int start = 0; start < nodes; ++start) {
+        for (;;) {
+            while (next[start] < adj[start].size() && used[adj[start][next[start]]]) ++next[start];
+            if (next[start] >= adj[start].size()) break;
+            int at = start, k = 0;          // walk a closed trail from `start`
+            for (;;) {
+                while (next[at] < adj[at].size() && used[adj[at][next[at]]]) ++next[at];
+                if (next[at] >= adj[at].size()) break;      // only possible back at `start`
+                const int e = adj[at][next[at]];
+                used[e] = 1;
+                col[e] = k++ & 1;
+                at = edges[e].a == at ? edges[e].b : edges[e].a;
+            }
+        }
+    }
+    colour.assign(E, 0);
+    for (int e = 0; e < E; ++e) colour[e] = col[e];
+}
+
 static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *out) {
     std::lock_guard<std::mutex> lock(c->sched_mu);
     auto it = c->bp_lr_sched.find({F, nwarps});
     if (it == c->bp_lr_sched.end()) {
         BpLrSchedule s;
-        // message slots in check-rank order: the checks of one degree class are stored back to back
+        // Message slots in check-rank order: the checks of one degree class are stored back to back.  With fewer than
+        // 16 frames per CTA a node's frames fill only part of a 128-byte line and the two (F = 8) nodes of a quarter-warp
+        // must use opposite halves of the line, i.e. slots of opposite parity, at every access:
+        //  * a class of even degree gets the stride degree + 1 (one idle slot per check), so consecutive checks -- the
+        //    lane groups of a step -- start on slots of alternating parity;
+        //  * the edges get a balanced 2-colouring (every node has as many edges of one colour as of the other, +-1:
+        //    Euler partition of the Tanner graph); a check lists its edges with alternating colours, so colour = slot
+        //    parity; variables are paired so that one has as many even slots as the other has odd ones and list their
+        //    edges in opposite parity order.
+        // The order of the nodes inside a degree class and of the edges inside a node only permutes independent work
+        // and the order of exact-in-any-order products' roundings; results stay deterministic.
+        const int pad_even = F < 16 ? 1 : 0;
+        std::vector<int> chk_ord(c->chk_order), var_ord(c->var_order);
+        std::vector<int> colour(c->E, 0);
+        if (pad_even) lr_balanced_colouring(c, colour);
         std::vector<int> slot_of_edge(c->E, 0), class_slot0;
+        int n_slots = 0;
         {
             int slot = 0;
             for (const BpClass &cl : c->chk_classes) {
+                const int stride = cl.degree | pad_even;
                 class_slot0.push_back(slot);
+                if (pad_even) {
+                    // order the checks of the class so that the majority colour of check k is the parity of its first slot
+                    std::vector<int> maj[2], out;
+                    for (int k = 0; k < cl.count; ++k) {
+                        const int chk = c->chk_order[cl.first + k];
+                        int ones = 0;
+                        for (int e = c->row_ptr[chk]; e < c->row_ptr[chk + 1]; ++e) ones += colour[e];
+                        maj[2 * ones > cl.degree ? 1 : 0].push_back(chk);
+                    }
+                    size_t i0 = 0, i1 = 0;
+                    for (int k = 0; k < cl.count; ++k) {
+                        const int want = (slot + k * stride) & 1;
+                        std::vector<int> &pref = maj[want], &other = maj[want ^ 1];
+                        size_t &ip = want ? i1 : i0, &io_ = want ? i0 : i1;
+                        if (ip < pref.size()) out.push_back(pref[ip++]);
+                        else out.push_back(other[io_++]);
+                    }
+                    for (int k = 0; k < cl.count; ++k) chk_ord[cl.first + k] = out[k];
+                }
                 for (int k = 0; k < cl.count; ++k) {
-                    const int chk = c->chk_order[cl.first + k];
-                    for (int e = c->row_ptr[chk]; e < c->row_ptr[chk + 1]; ++e) slot_of_edge[e] = slot++;
+                    const int chk = chk_ord[cl.first + k];
+                    const int e0 = c->row_ptr[chk], d = cl.degree;
+                    if (pad_even) {
+                        // positions of parity (slot & 1) take the edges of that colour first
+                        std::vector<int> by_col[2], pos_of(d, -1);
+                        for (int j = 0; j < d; ++j) by_col[colour[e0 + j]].push_back(j);
+                        std::vector<int> rest;
+                        size_t used[2] = {0, 0};
+                        for (int q = 0; q < d; ++q) {
+                            const int par = (slot + q) & 1;
+                            if (used[par] < by_col[par].size()) pos_of[by_col[par][used[par]++]] = q;
+                            else rest.push_back(q);
+                        }
+                        size_t r = 0;
+                        for (int j = 0; j < d; ++j)
+                            if (pos_of[j] < 0) pos_of[j] = rest[r++];
+                        for (int j = 0; j < d; ++j) slot_of_edge[e0 + j] = slot + pos_of[j];
+                    } else {
+                        for (int j = 0; j < d; ++j) slot_of_edge[e0 + j] = slot + j;
+                    }
+                    slot += stride;
                 }
             }
+            n_slots = std::max(slot, 1);
+        }
+        // variable order inside a class: pairs (2i, 2i+1) with complementary numbers of even slots
+        std::vector<std::vector<int>> var_edges(c->n);      // the edges of a variable in record order
+        for (const BpClass &cl : c->var_classes) {
+            std::vector<int> members(c->var_order.begin() + cl.first, c->var_order.begin() + cl.first + cl.count);
+            auto evens = [&](int v) {
+                int k = 0;
+                for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) k += !(slot_of_edge[c->csc_edge[q]] & 1);
+                return k;
+            };
+            std::vector<int> order;
+            if (pad_even) {
+                std::vector<std::vector<int>> bucket(cl.degree + 1);
+                for (int v : members) bucket[evens(v)].push_back(v);
+                std::vector<int> left;
+                for (int t = 0; t <= cl.degree; ++t) {
+                    std::vector<int> &a = bucket[t], &b = bucket[cl.degree - t];
+                    if (t > cl.degree - t) break;
+                    if (t == cl.degree - t) {
+                        while (a.size() >= 2) { order.push_back(a.back()); a.pop_back(); order.push_back(a.back()); a.pop_back(); }
+                    } else {
+                        while (!a.empty() && !b.empty()) { order.push_back(a.back()); a.pop_back(); order.push_back(b.back()); b.pop_back(); }
+                    }
+                }
+                for (auto &bk : bucket) for (int v : bk) left.push_back(v);
+                order.insert(order.end(), left.begin(), left.end());
+            } else {
+                order = members;
+            }
+            for (int k = 0; k < cl.count; ++k) {
+                const int v = order[k];
+                var_ord[cl.first + k] = v;
+                std::vector<int> ev, od;
+                for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) {
+                    const int e = c->csc_edge[q];
+                    ((slot_of_edge[e] & 1) ? od : ev).push_back(e);
+                }
+                std::vector<int> &first = (pad_even && (k & 1)) ? od : ev, &second = (pad_even && (k & 1)) ? ev : od;
+                if (pad_even) {
+                    var_edges[v] = first;
+                    var_edges[v].insert(var_edges[v].end(), second.begin(), second.end());
+                } else {
+                    for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1]; ++q) var_edges[v].push_back(c->csc_edge[q]);
+                }
+            }
+        }
+        // L_ch / decision / posterior storage in variable-rank order (neighbouring lane groups -> neighbouring rows);
+        // variables without edges follow
+        std::vector<uint16_t> var_store(c->n, 0);
+        {
+            std::vector<char> ranked(c->n, 0);
+            int next = 0;
+            for (int v : var_ord) { var_store[v] = (uint16_t) next++; ranked[v] = 1; }
+            for (int v = 0; v < c->n; ++v)
+                if (!ranked[v]) var_store[v] = (uint16_t) next++;
         }
         // variable records in rank order (classes of equal degree are adjacent, code.cu)
         std::vector<uint32_t> rec, first_v;
@@ -452,21 +608,30 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
             first_v.push_back((uint32_t) rec.size() * 4);     // byte offset
             const int stride = ((cl.degree + 1 + 3) / 4) * 4;
             for (int k = 0; k < cl.count; ++k) {
-                const int v = c->var_order[cl.first + k];
+                const int v = var_ord[cl.first + k];
                 const size_t base = rec.size();
                 rec.resize(base + stride, 0u);
-                rec[base] = (uint32_t) v * F * 8;
-                for (int j = 0; j < cl.degree; ++j)
-                    rec[base + 1 + j] = (uint32_t) slot_of_edge[c->csc_edge[c->col_ptr[v] + j]] * F * 8;
+                rec[base] = (uint32_t) var_store[v] * F * 8;
+                for (int j = 0; j < cl.degree; ++j) rec[base + 1 + j] = (uint32_t) slot_of_edge[var_edges[v][j]] * F * 8;
             }
         }
-        if (rec.size() * 4 >= (1u << 18) || (size_t) c->E * F * 8 >= (1u << 18))
+        if (const char *dbg = getenv("LDPC_BP_LAYOUT_STATS")) {
+            (void) dbg;
+            // replayed accesses of the variable pass: pairs (2i, 2i+1) of a class whose j-th slots have equal parity
+            long clash = 0, total = 0;
+            for (const BpClass &cl : c->var_classes)
+                for (int k = 0; k + 1 < cl.count; k += 2)
+                    for (int j = 0; j < cl.degree; ++j, ++total)
+                        clash += !((slot_of_edge[var_edges[var_ord[cl.first + k]][j]] ^ slot_of_edge[var_edges[var_ord[cl.first + k + 1]][j]]) & 1);
+            fprintf(stderr, "bp layout F=%d: %ld of %ld paired variable-pass accesses share a half line\n", F, clash, total);
+        }
+        if (rec.size() * 4 >= (1u << 18) || (size_t) n_slots * F * 8 >= (1u << 18))
             return fail(LDPC_E_UNSUPPORTED, "code too large for the 18-bit step offsets of the BP kernel");
         auto sv = deal_steps(c->var_classes, F, nwarps, [&](int cls, int node0) {
             return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 16);
         });
         auto sc = deal_steps(c->chk_classes, F, nwarps, [&](int cls, int node0) {
-            return (uint32_t) (class_slot0[cls] + node0 * c->chk_classes[cls].degree) * F * 8;
+            return (uint32_t) (class_slot0[cls] + node0 * (c->chk_classes[cls].degree | pad_even)) * F * 8;
         });
         size_t mv = 1, mc = 1;
         for (int w = 0; w < nwarps; ++w) { mv = std::max(mv, sv[w].size() + 1); mc = std::max(mc, sc[w].size() + 1); }
@@ -476,9 +641,12 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
             std::copy(sc[w].begin(), sc[w].end(), steps.begin() + (size_t) w * (mv + mc) + mv);
         }
         s.rec_words = (int) rec.size();
+        s.n_slots = n_slots;
+        s.pad_even = pad_even;
         s.steps_per_warp = (int) (mv + mc);
         s.steps_c_off = (int) mv;
         int st;
+        if ((st = upload_vec(&s.var_store, var_store))) return st;
         if ((st = upload_vec(&s.rec_v, rec))) return st;
         if ((st = upload_vec(&s.steps, steps))) return st;
         it = c->bp_lr_sched.emplace(std::make_pair(F, nwarps), s).first;
@@ -494,7 +662,8 @@ static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, int64_t 
     if (st) return st;
     p.rec_v = s.rec_v; p.steps = s.steps; p.rec_words = s.rec_words;
     p.steps_per_warp = s.steps_per_warp; p.steps_c_off = s.steps_c_off;
-    const size_t smem = lr_smem_bytes(c, F, p.soft != 0, p.io.experiment != 0, s.rec_words, s.steps_per_warp * (threads / 32));
+    p.var_store = s.var_store; p.pad_even = s.pad_even; p.E = s.n_slots;      // message slots including the idle ones
+    const size_t smem = lr_smem_bytes(c, s.n_slots, F, p.soft != 0, p.io.experiment != 0, s.rec_words, s.steps_per_warp * (threads / 32));
     if (smem > 227 * 1024) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
     auto kernel = bp_lr_kernel<F, MAXT>;
     LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -545,18 +714,21 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     }
     const bool exp_mode = fio.experiment != 0;
     const int rec_words = rec_words_of(c);
-    int F = 16;
+    // Frames per CTA.  Two CTAs of 8 frames per SM beat one CTA of 16 (47.0 vs 50.5 ms, profiles/r01_bp_lr_sweep.txt): the
+    // FP64-bound check pass of one overlaps the shared-memory-bound variable pass of the other, and the parity layout
+    // of get_lr_schedule keeps the 64-byte rows of F = 8 conflict-free.
+    int F = 8;
     if (const char *force = getenv("LDPC_BP_F")) {
         const int v = atoi(force);
         if (v == 2 || v == 4 || v == 8 || v == 16) F = v;
     } else {
         while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
     }
-    while (F > 2 && lr_smem_bytes(c, F, p.soft, exp_mode, rec_words, 64 * 24) > 227 * 1024) F >>= 1;
-    // warps per CTA: about three steps per warp and pass (measured on B200: throughput is flat from 16 to 24 warps,
-    // profiles/r01_bp_lr_sweep.txt; more warps hide the barrier and shared-memory latencies of the short passes)
+    while (F > 2 && lr_smem_bytes(c, c->E + c->m, F, p.soft, exp_mode, rec_words, 64 * 24) > 227 * 1024) F >>= 1;
+    // warps per CTA: about three steps per warp and pass; at most 256 threads for F <= 8 so that two CTAs of the
+    // 128-register variant share an SM
     const int lanes = std::max(c->n, c->m) * (F / 2);
-    int threads = std::min(768, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
+    int threads = std::min(F >= 16 ? 768 : 256, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
         if (v >= 32 && v <= 768) threads = v;

@@ -168,7 +168,7 @@ void ldpc_code_destroy(ldpc_code_t *c) {
     free_chk_tables(c);
     for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
     for (auto &kv : c->bp_lr_sched) {
-        cudaFree(kv.second.rec_v); cudaFree(kv.second.steps);
+        cudaFree(kv.second.rec_v); cudaFree(kv.second.steps); cudaFree(kv.second.var_store);
     }
     delete c;
 }

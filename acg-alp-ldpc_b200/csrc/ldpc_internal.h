@@ -50,7 +50,8 @@ struct BpSchedule {   // device arrays, rounds x warps jobs each (log-domain ker
 struct BpLrSchedule {
     uint32_t *rec_v = nullptr;    // variable node records
     uint32_t *steps = nullptr;    // per warp: variable-pass steps, check-pass steps (bp_lr_kernel.cu: lr_step_word)
-    int rec_words = 0, steps_per_warp = 0, steps_c_off = 0;
+    uint16_t *var_store = nullptr; // variable index -> storage index of its per-variable arrays
+    int rec_words = 0, steps_per_warp = 0, steps_c_off = 0, n_slots = 0, pad_even = 0;
 };
 
 // QP-ADMM works per BLOCK: one three-variable check of the chain decomposition
