@@ -375,6 +375,11 @@ int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *
     return debug_bpmath(device, count, a, ev, od, out_exp, out_log);
 }
 
+int ldpc_debug_bp_layout(const ldpc_code_t *c, int32_t frames_per_cta, int32_t out[6]) {
+    if (!c || !out) return fail(LDPC_E_INVALID, "NULL argument");
+    return bp_lr_layout_stats(c, frames_per_cta, out);
+}
+
 int ldpc_measure_smem_peak(int device, double *gbytes_per_s) {
     if (!gbytes_per_s) return fail(LDPC_E_INVALID, "NULL argument");
     return measure_smem_peak(device, gbytes_per_s);

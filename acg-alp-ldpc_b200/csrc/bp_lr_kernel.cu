@@ -615,16 +615,21 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                 for (int j = 0; j < cl.degree; ++j) rec[base + 1 + j] = (uint32_t) slot_of_edge[var_edges[v][j]] * F * 8;
             }
         }
-        if (const char *dbg = getenv("LDPC_BP_LAYOUT_STATS")) {
-            (void) dbg;
-            // replayed accesses of the variable pass: pairs (2i, 2i+1) of a class whose j-th slots have equal parity
-            long clash = 0, total = 0;
-            for (const BpClass &cl : c->var_classes)
-                for (int k = 0; k + 1 < cl.count; k += 2)
-                    for (int j = 0; j < cl.degree; ++j, ++total)
-                        clash += !((slot_of_edge[var_edges[var_ord[cl.first + k]][j]] ^ slot_of_edge[var_edges[var_ord[cl.first + k + 1]][j]]) & 1);
-            fprintf(stderr, "bp layout F=%d: %ld of %ld paired variable-pass accesses share a half line\n", F, clash, total);
+        // layout statistics: paired accesses (lane groups 2i, 2i+1 of a class, same edge position) whose slots have
+        // equal parity, i.e. replayed wavefronts at F = 8
+        int clash_v = 0, pairs_v = 0, clash_c = 0, pairs_c = 0;
+        for (const BpClass &cl : c->var_classes)
+            for (int k = 0; k + 1 < cl.count; k += 2)
+                for (int j = 0; j < cl.degree; ++j, ++pairs_v)
+                    clash_v += !((slot_of_edge[var_edges[var_ord[cl.first + k]][j]] ^ slot_of_edge[var_edges[var_ord[cl.first + k + 1]][j]]) & 1);
+        for (size_t ci = 0; ci < c->chk_classes.size(); ++ci) {
+            const BpClass &cl = c->chk_classes[ci];
+            for (int k = 0; k + 1 < cl.count; k += 2, pairs_c += cl.degree)
+                clash_c += ((cl.degree | pad_even) & 1) ? 0 : cl.degree;
         }
+        if (getenv("LDPC_BP_LAYOUT_STATS"))
+            fprintf(stderr, "bp layout F=%d: %d of %d paired variable-pass and %d of %d paired check-pass accesses share a half line\n",
+                    F, clash_v, pairs_v, clash_c, pairs_c);
         if (rec.size() * 4 >= (1u << 18) || (size_t) n_slots * F * 8 >= (1u << 18))
             return fail(LDPC_E_UNSUPPORTED, "code too large for the 18-bit step offsets of the BP kernel");
         auto sv = deal_steps(c->var_classes, F, nwarps, [&](int cls, int node0) {
@@ -643,6 +648,7 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
         s.rec_words = (int) rec.size();
         s.n_slots = n_slots;
         s.pad_even = pad_even;
+        s.clash_v = clash_v; s.pairs_v = pairs_v; s.clash_c = clash_c; s.pairs_c = pairs_c;
         s.steps_per_warp = (int) (mv + mc);
         s.steps_c_off = (int) mv;
         int st;
@@ -677,6 +683,17 @@ static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, int64_t 
     p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * 4 * F) * F));
     kernel<<<(unsigned) grid, threads, smem, stream>>>(p);
     LDPC_CUDA(cudaGetLastError());
+    return LDPC_OK;
+}
+
+// testing hook: statistics of the shared-memory layout for F frames per CTA (ldpc_debug_bp_layout)
+int bp_lr_layout_stats(const ldpc_code *c, int F, int32_t out[6]) {
+    if (F != 2 && F != 4 && F != 8 && F != 16) return fail(LDPC_E_INVALID, "F must be 2, 4, 8 or 16");
+    BpLrSchedule s;
+    LDPC_CUDA(cudaSetDevice(c->device));
+    int st = get_lr_schedule(c, F, 8, &s);
+    if (st) return st;
+    out[0] = s.n_slots; out[1] = s.pad_even; out[2] = s.clash_v; out[3] = s.pairs_v; out[4] = s.clash_c; out[5] = s.pairs_c;
     return LDPC_OK;
 }
 

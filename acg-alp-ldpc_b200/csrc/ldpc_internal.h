@@ -52,6 +52,7 @@ struct BpLrSchedule {
     uint32_t *steps = nullptr;    // per warp: variable-pass steps, check-pass steps (bp_lr_kernel.cu: lr_step_word)
     uint16_t *var_store = nullptr; // variable index -> storage index of its per-variable arrays
     int rec_words = 0, steps_per_warp = 0, steps_c_off = 0, n_slots = 0, pad_even = 0;
+    int clash_v = 0, pairs_v = 0, clash_c = 0, pairs_c = 0;   // layout statistics (ldpc_debug_bp_layout)
 };
 
 // QP-ADMM works per BLOCK: one three-variable check of the chain decomposition
@@ -153,6 +154,7 @@ int launch_bp_lr(const ldpc_code *code, const FrameIO &io, int64_t frames, doubl
 int launch_bp_log(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, int max_iter,
                   int early_exit, unsigned long long *queue, cudaStream_t stream);
 double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
+int bp_lr_layout_stats(const ldpc_code *code, int F, int32_t out[6]);
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
 // the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 3..8) and block-per-lane (any code)

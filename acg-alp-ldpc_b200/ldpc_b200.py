@@ -75,6 +75,7 @@ def lib():
     L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
     L.ldpc_measure_smem_peak.argtypes = [C.c_int, C.POINTER(dbl)]
     L.ldpc_debug_bpmath.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
+    L.ldpc_debug_bp_layout.argtypes = [vp, i32, vp]
     _lib = L
     return L
 
@@ -211,6 +212,12 @@ class Code:
         res["gpu_seconds"] = secs.value
         return res
 
+
+    def bp_layout(self, frames_per_cta):
+        """layout statistics of the likelihood-ratio BP kernel (ldpc_debug_bp_layout)"""
+        out = np.zeros(6, np.int32)
+        _check(lib().ldpc_debug_bp_layout(self._h, frames_per_cta, out.ctypes.data))
+        return dict(zip(("slots", "pad_even", "clash_v", "pairs_v", "clash_c", "pairs_c"), (int(x) for x in out)))
 
     def qpadmm_grid(self, alphas, mus, snr, max_iter, eps_stop, seed, frame_begin, frame_count, source=CW_ZERO,
                     words=None):

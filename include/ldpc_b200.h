@@ -197,6 +197,12 @@ int ldpc_measure_smem_peak(int device, double *gbytes_per_s);
 int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *ev, const double *od,
                       double *out_exp, double *out_log);
 
+/* ---- testing hook: the shared-memory layout of the likelihood-ratio BP kernel for `frames_per_cta` (2, 4, 8, 16)
+ * frames per CTA.  out = {message slots per frame, 1 if even-degree check classes are padded to an odd stride,
+ * variable-pass accesses of paired lane groups that share a half line, ... examined, the same two numbers for the
+ * check pass}.  With 8 frames per CTA a shared half line is a replayed shared-memory wavefront. */
+int ldpc_debug_bp_layout(const ldpc_code_t *code, int32_t frames_per_cta, int32_t out[6]);
+
 #ifdef __cplusplus
 }
 #endif

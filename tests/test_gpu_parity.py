@@ -352,3 +352,16 @@ def test_qpadmm_grid_equals_point_by_point(codes, oracle):
     # and one pair against the CPU oracle's replay
     want = oracle.experiment("qpadmm", csr, m, n, snr, iters, SEED, 11, frames, alpha=1.2, mu=0.55, eps_stop=eps)
     assert all(grid[1][k] == want[k] for k in want)
+
+
+@pytest.mark.gpu
+def test_bp_layout_for_8_frames_per_cta_is_nearly_conflict_free(codes):
+    """odd class strides + balanced edge 2-colouring: paired lane groups use opposite halves of a 128-byte line"""
+    for name in ("optimalH", "H05", "reg_3_6_1008"):
+        H, code, csr = codes[name]
+        st = code.bp_layout(8)
+        print(name, st)
+        assert st["pad_even"] == 1 and st["slots"] >= int(H.sum())
+        assert st["clash_c"] == 0
+        assert st["clash_v"] <= 0.12 * st["pairs_v"], st
+        assert code.bp_layout(16)["slots"] == int(H.sum())        # 16 frames fill a line: no padding
