@@ -103,16 +103,19 @@ int decode_host(const ldpc_code *c, const DecodeCfg &cfg, const double *y, int64
     // chunk: <= 256 MiB of y per slot, and at least a few waves of CTAs
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(frames, (256ll << 20) / (int64_t) (n * sizeof(double))));
     if (frames > chunk && frames < 2 * chunk) chunk = (frames + 1) / 2;
+    if ((int64_t) (frames * n * sizeof(double)) >= (64ll << 20))
+        chunk = std::min<int64_t>(chunk, (frames + 3) / 4);   // large batches: at least four chunks, so copies overlap kernels
     int st;
     for (int s = 0; s < 2; ++s) {
         if ((st = slot_init(slots[s]))) return st;
-        if (s == 0 || frames > chunk)
-            if ((st = slot_reserve(slots[s], (size_t) chunk, n, soft != nullptr))) return st;
+        if ((st = slot_reserve(slots[s], (size_t) chunk, n, soft != nullptr))) return st;
     }
+    // the first chunk is small: its copy-in is the only one no kernel hides
     int which = 0;
-    for (int64_t begin = 0; begin < frames; begin += chunk, which ^= 1) {
+    int64_t cnt = 0;
+    for (int64_t begin = 0; begin < frames; begin += cnt, which ^= 1) {
         Slot &s = slots[which];
-        const int64_t cnt = std::min(chunk, frames - begin);
+        cnt = std::min(begin == 0 && frames > chunk ? std::max<int64_t>(chunk / 8, 1) : chunk, frames - begin);
         LDPC_CUDA(cudaMemcpyAsync(s.y, y + begin * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, s.stream));
         FrameIO io;
         io.y = s.y; io.bits = s.bits; io.ok = s.ok; io.iters = s.iters; io.soft = soft ? s.soft : nullptr;
@@ -125,7 +128,7 @@ int decode_host(const ldpc_code *c, const DecodeCfg &cfg, const double *y, int64
                                       s.stream));
     }
     LDPC_CUDA(cudaStreamSynchronize(slots[0].stream));
-    if (frames > chunk) LDPC_CUDA(cudaStreamSynchronize(slots[1].stream));
+    LDPC_CUDA(cudaStreamSynchronize(slots[1].stream));
     return LDPC_OK;
 }
 

@@ -46,7 +46,7 @@
 #include <cstring>
 
 #include "bpmath.cuh"
-#include "slots.cuh"
+#include "slots_multi.cuh"
 
 namespace ldpc {
 
@@ -277,17 +277,13 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         const unsigned okmask = ctl->elig & ~ctl->bad & active;          // syndrome vanished (iteration >= 1)
         const unsigned finmask = (ctl->atmax | (p.early_exit ? okmask : 0u)) & active;
         if (finmask || trip == 0) {
-            for (int f = 0; f < F; ++f) {
-                if (!((finmask >> f) & 1u)) continue;
-                const int ok = (okmask >> f) & 1u;
-                const uint8_t *df = dec + f;
-                const char *pf = post + f * 8;
-                slot_finish<F>(io, S, f, ok, ok, ok, S->iter[f], cw, [&](int i) { return (int) df[(size_t) p.var_store[i] * F]; },
-                               [&](int i) {
-                                   const double t = ld_f64(pf + (size_t) p.var_store[i] * FB);
-                                   return log_pos(fmin(fmax(t, 1e-300), 1e300));
-                               });
-            }
+            if (finmask)
+                slots_finish_all<F>(io, S, finmask, okmask, cw,
+                                    [&](int i, int f) { return (int) dec[(size_t) p.var_store[i] * F + f]; },
+                                    [&](int i, int f) {
+                                        const double t = ld_f64(post + (size_t) p.var_store[i] * FB + f * 8);
+                                        return log_pos(fmin(fmax(t, 1e-300), 1e300));
+                                    });
             __syncthreads();
             if (warp == 0) {
                 // lanes f < F own slot f: empty slots take the next frame of the locally claimed range
@@ -332,7 +328,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
                 for (int i = tid; i < p.E * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) st_f64(msg + (size_t) i * 8, 1.0);
                 // L_ch = exp(llr), llr clamped to +-llr_cap; variables without edges keep decision / posterior of the channel
-                slots_load<F>(io, S, fresh, nullptr, 0, cw, [&](int i, int f, double l) {
+                slots_load_all<F>(io, S, fresh, cw, [&](int i, int f, double l) {
                     const double lc = exp_signed(fmin(fmax(l, -p.llr_cap), p.llr_cap));
                     const size_t st = p.var_store[i];
                     st_f64(lch + st * FB + f * 8, lc);
