@@ -738,10 +738,11 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
         while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
     }
     while (F > 2 && lr_smem_bytes(c, c->E + c->m, F, p.soft, exp_mode, rec_words, 64 * 24) > 227 * 1024) F >>= 1;
-    // warps per CTA: about three steps per warp and pass; at most 256 threads for F <= 8 so that two CTAs of the
-    // 128-register variant share an SM
+    // warps per CTA: about three steps per warp and pass; at most 256 threads when two CTAs fit an SM, so that both
+    // run the 128-register variant
     const int lanes = std::max(c->n, c->m) * (F / 2);
-    int threads = std::min(F >= 16 ? 768 : 256, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
+    const bool two_ctas = 2 * lr_smem_bytes(c, c->E + c->m, F, p.soft, exp_mode, rec_words, 64 * 24) <= 227 * 1024;
+    int threads = std::min(two_ctas ? 256 : 768, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
         if (v >= 32 && v <= 768) threads = v;

@@ -366,3 +366,45 @@ def test_bp_layout_for_8_frames_per_cta_is_nearly_conflict_free(codes):
         assert st["clash_v"] <= 0.12 * st["pairs_v"], st
         if name != "reg_3_6_1008":     # (16 frames of the n = 1008 code exceed the kernel's shared-memory offsets)
             assert code.bp_layout(16)["slots"] == int(H.sum())        # 16 frames fill a line: no padding
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_row_deg", [10, 12, 16])
+def test_wide_check_degrees(gpu_lib, oracle, max_row_deg):
+    """checks of degree 9..12 take the check-centric QP-ADMM kernel's wide variants and the generic-degree paths of the
+    likelihood-ratio BP kernel; degree 16 takes the fallbacks (block-per-lane QP-ADMM, log-domain BP)"""
+    rng = np.random.default_rng(100 + max_row_deg)
+    m, n = 24, 60
+    H = np.zeros((m, n), np.uint8)
+    degs = [3, 4, 5, 6, 7, 8, 9, max_row_deg] * 3
+    for r, d in enumerate(degs):
+        H[r, rng.choice(n, size=d, replace=False)] = 1
+    for v in np.flatnonzero(H.sum(0) == 0):          # every variable in at least one check
+        H[rng.integers(m), v] = 1
+    code = gpu_lib.Code(H=H)
+    csr = dense_to_csr(H)
+    y = 1.0 + 0.75 * rng.standard_normal((64, n))
+    snr = 0.0
+    gb, gok, git, gv = code.qpadmm_decode(y, snr, 1.2, 0.55, 400, 1e-5)
+    ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, 1.2, 0.55, 400, 1e-5)
+    assert (gb == ob).all() and (gok == ook).all() and (git == oit).all() and (gv == ov).all()
+    gb, gok, git, gpost = code.bp_decode(y, snr, 50)
+    ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, snr, 50)
+    assert (gb == ob).all() and (gok == ook).all() and (git == oit).all()
+    fin = np.isfinite(opost) & (np.abs(opost) < 30) & (ook == 1)[:, None]
+    assert np.allclose(gpost[fin], opost[fin], rtol=1e-4, atol=0)
+    code.close()
+
+
+@pytest.mark.gpu
+def test_qpadmm_block_kernel_fallback(codes, oracle, monkeypatch):
+    """the block-per-lane kernel (codes outside the check-centric kernel's range) stays bit-identical to the oracle"""
+    monkeypatch.setenv("LDPC_ADMM_KERNEL", "block")
+    for name, frames, snr, iters in (("optimalH", 75, -3.0, 600), ("reg_3_6_1008", 9, -1.0, 200)):
+        H, code, csr = codes[name]
+        m, n = H.shape
+        alpha, mu = ADMM[name]
+        y = code.channel(SEED, 9000, frames, snr)
+        gb, gok, git, gv = code.qpadmm_decode(y, snr, alpha, mu, iters, 1e-5)
+        ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, iters, 1e-5)
+        assert (git == oit).all() and (gb == ob).all() and (gok == ook).all() and (gv == ov).all(), name
