@@ -39,6 +39,10 @@ ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
 BP_FP64_PER_EDGE_ITER = 12.0          # check: 5.3 Pe/Po recurrences + 5 division; variable: 2.7 products + decision
 BP_SMEM_BYTES_PER_EDGE_ITER = 32.0    # each message is read and written once per pass (8 B), two passes
 BP_SMEM_BYTES_PER_VAR_ITER = 8.0      # channel likelihood ratio
+# DRAM traffic per frame from the ncu --set full captures of the two kernels (dram__bytes_read.sum + dram__bytes_write.sum
+# over the frames of the captured launch, profiles/r01_bp_lr_final_ncu.txt / r01_admm_chk_final_ncu.txt): the y samples
+# (n x 8 B = 2240 B) and nothing else -- the outputs stay in L2 until after the kernel
+NCU_DRAM_BYTES_PER_FRAME = {"bp": 10.724e6 / 4736, "qpadmm": 5.396e6 / 2368}
 # QP-ADMM, check-centric kernel: per three-variable block and iteration
 ADMM_FP64_PER_BLOCK_ITER = 47.0       # 9 residual + 25 row updates (6 per row, 7 for row 3) + 6.5 auxiliary update + 6.5 variable update
 
@@ -299,12 +303,12 @@ def run_gpu(args):
             smem_bytes = info["edges"] * BP_SMEM_BYTES_PER_EDGE_ITER + info["n"] * BP_SMEM_BYTES_PER_VAR_ITER
             got = fps_gpu * n_iter * smem_bytes / 1e9
             roof = {"bound": "smem", "achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
-                    "traffic": None, "bytes_per_frame_iter": smem_bytes,
+                    "traffic": NCU_DRAM_BYTES_PER_FRAME["bp"] * frames, "bytes_per_frame_iter": smem_bytes,
                     "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)",
                     "work_per_launch": "%d frames x %d iters x %.0f B of shared-memory traffic" % (frames, n_iter, smem_bytes),
                     "fp64": fp64, "hbm": hbm}
         else:
-            roof = dict(fp64, bound="fp64", traffic=None, hbm=hbm)
+            roof = dict(fp64, bound="fp64", traffic=NCU_DRAM_BYTES_PER_FRAME["qpadmm"] * frames, hbm=hbm)
         res = {
             "value": value, "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
             "info_gbit_per_s": value * k / 1e9,
