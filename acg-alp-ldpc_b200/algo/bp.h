@@ -12,12 +12,12 @@ public:
     explicit BeliefPropagationDecoder(int max_iter) : _max_iter(max_iter) {}
 
     pair<TCodeword, bool> decode(const TMatrix &H, const TFVector &channel_word, double snr) override {
-        ldpc_code_t *code = ldpc_host::CodeCache::instance().get(H);
+        ldpc_host::CodeRef code = ldpc_host::CodeCache::instance().get(H);
         const size_t n = channel_word.size();
         vector<uint8_t> bits(n);
         uint8_t ok = 0;
         int32_t iters = 0;
-        if (ldpc_bp_decode(code, channel_word.data(), 1, snr, _max_iter, 1, bits.data(), &ok, &iters, nullptr))
+        if (ldpc_bp_decode(code.get(), channel_word.data(), 1, snr, _max_iter, 1, bits.data(), &ok, &iters, nullptr))
             ldpc_host::die("ldpc_bp_decode");
         if (!ok) return {TCodeword(), false};
         return {TCodeword(bits.begin(), bits.end()), true};

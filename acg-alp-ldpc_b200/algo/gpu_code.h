@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include "algo.h"
@@ -43,6 +44,10 @@ inline CsrMatrix to_csr(const TMatrix &H) {
     return c;
 }
 
+// A handle stays alive while somebody holds the shared_ptr: the cache may evict it while another host thread is still
+// decoding with it (optimize_H.cpp evaluates several proposals, i.e. several H, concurrently).
+typedef shared_ptr<ldpc_code_t> CodeRef;
+
 class CodeCache {
 public:
     static CodeCache &instance() {
@@ -50,15 +55,17 @@ public:
         return cache;
     }
 
-    ldpc_code_t *get(const TMatrix &H, int device = 0) {
+    CodeRef get(const TMatrix &H, int device = 0) {
         CsrMatrix key = to_csr(H);
         lock_guard<mutex> lock(mu_);
-        auto &slot = codes_[make_pair(device, key)];
+        CodeRef &slot = codes_[make_pair(device, key)];
         if (!slot) {
             vector<int32_t> cols = key.col_idx;
             if (cols.empty()) cols.push_back(0);
-            if (ldpc_code_create(key.m, key.n, key.row_ptr.data(), cols.data(), device, &slot) != LDPC_OK)
+            ldpc_code_t *raw = nullptr;
+            if (ldpc_code_create(key.m, key.n, key.row_ptr.data(), cols.data(), device, &raw) != LDPC_OK)
                 die("ldpc_code_create");
+            slot = CodeRef(raw, [](ldpc_code_t *c) { ldpc_code_destroy(c); });
             if (codes_.size() > 64) evict(device, key);   // optimize_H.cpp proposes a new H every step
         }
         return slot;
@@ -68,11 +75,11 @@ private:
     void evict(int device, const CsrMatrix &keep) {
         for (auto it = codes_.begin(); it != codes_.end();) {
             if (it->first.first == device && !(it->first.second < keep) && !(keep < it->first.second)) ++it;
-            else { ldpc_code_destroy(it->second); it = codes_.erase(it); }
+            else it = codes_.erase(it);                   // destroyed when its last user lets go
         }
     }
     mutex mu_;
-    map<pair<int, CsrMatrix>, ldpc_code_t *> codes_;
+    map<pair<int, CsrMatrix>, CodeRef> codes_;
 };
 
 inline int visible_gpus() {

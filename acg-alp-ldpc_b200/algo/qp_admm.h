@@ -14,12 +14,12 @@ public:
         : _alpha(alpha), _mu(mu), _eps_stop(eps_stop), _max_iter(max_iter) {}
 
     pair<TCodeword, bool> decode(const TMatrix &H, const TFVector &channel_word, double snr) override {
-        ldpc_code_t *code = ldpc_host::CodeCache::instance().get(H);
+        ldpc_host::CodeRef code = ldpc_host::CodeCache::instance().get(H);
         const size_t n = channel_word.size();
         vector<uint8_t> bits(n);
         uint8_t ok = 0;
         int32_t iters = 0;
-        if (ldpc_qpadmm_decode(code, channel_word.data(), 1, snr, _alpha, _mu, _max_iter, _eps_stop, bits.data(), &ok,
+        if (ldpc_qpadmm_decode(code.get(), channel_word.data(), 1, snr, _alpha, _mu, _max_iter, _eps_stop, bits.data(), &ok,
                                &iters, nullptr))
             ldpc_host::die("ldpc_qpadmm_decode");
         return {TCodeword(bits.begin(), bits.end()), ok != 0};

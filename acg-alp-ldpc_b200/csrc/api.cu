@@ -28,6 +28,20 @@ struct Slot {
 
 struct ThreadCtx {
     std::map<int, Slot[2]> per_device;
+    // host threads come and go (optimize_H.cpp evaluates proposals on short-lived threads): give the streams and
+    // buffers back when the thread ends (errors are ignored: at process exit the runtime may already be gone)
+    ~ThreadCtx() {
+        for (auto &kv : per_device) {
+            if (cudaSetDevice(kv.first) != cudaSuccess) continue;
+            for (Slot &s : kv.second) {
+                if (s.stream) cudaStreamSynchronize(s.stream);
+                cudaFree(s.queue); cudaFree(s.counters); cudaFree(s.y); cudaFree(s.soft);
+                cudaFree(s.bits); cudaFree(s.ok); cudaFree(s.iters);
+                if (s.stream) cudaStreamDestroy(s.stream);
+            }
+        }
+        cudaGetLastError();
+    }
 };
 
 thread_local ThreadCtx g_ctx;

@@ -104,13 +104,30 @@ inline ExperimentResult from_counters(const uint64_t *c, double seconds) {
     return r;
 }
 
-// One Monte-Carlo point on all visible GPUs; frame f transmits codewords[f].
+// Pins the experiments of the calling host thread to one GPU (-1: frames are split over all visible GPUs).
+// optimize_H.cpp evaluates several proposals concurrently, one host thread and one GPU per proposal.
+inline int &pinned_gpu() {
+    static thread_local int device = -1;
+    return device;
+}
+
+// One Monte-Carlo point on all visible GPUs (or on the pinned one); frame f transmits codewords[f].
 inline ExperimentResult gpu_experiment(const GpuDecoder &decoder, const vector<TCodeword> &codewords, const TMatrix &H,
                                        double snr) {
     const size_t frames = codewords.size(), n = H[0].size();
     vector<uint8_t> words(frames * n);
     for (size_t f = 0; f < frames; ++f)
         for (size_t i = 0; i < n; ++i) words[f * n + i] = codewords[f][i];
+    if (pinned_gpu() >= 0) {
+        CodeRef code = CodeCache::instance().get(H, pinned_gpu());
+        const ldpc_algo_cfg_t cfg1 = decoder.config();
+        uint64_t cnt[LDPC_CNT_COUNT];
+        double secs = 0;
+        if (ldpc_experiment_run(code.get(), &cfg1, snr, experiment_seed(), 0, frames, LDPC_CW_TABLE, words.data(), frames, cnt,
+                                &secs) != LDPC_OK)
+            die("ldpc_experiment_run");
+        return from_counters(cnt, secs);
+    }
     const int gpus = max(1, min<int>(visible_gpus(), (int) max<size_t>(frames, 1)));
     const ldpc_algo_cfg_t cfg = decoder.config();
     const uint64_t seed = experiment_seed();
@@ -119,10 +136,10 @@ inline ExperimentResult gpu_experiment(const GpuDecoder &decoder, const vector<T
     for (int g = 0; g < gpus; ++g)
         workers.emplace_back([&, g] {
             const uint64_t begin = frames * g / gpus, end = frames * (g + 1) / gpus;
-            ldpc_code_t *code = CodeCache::instance().get(H, g);
+            CodeRef code = CodeCache::instance().get(H, g);
             uint64_t cnt[LDPC_CNT_COUNT];
             double secs = 0;
-            if (ldpc_experiment_run(code, &cfg, snr, seed, begin, end - begin, LDPC_CW_TABLE, words.data(), frames, cnt,
+            if (ldpc_experiment_run(code.get(), &cfg, snr, seed, begin, end - begin, LDPC_CW_TABLE, words.data(), frames, cnt,
                                     &secs) != LDPC_OK)
                 die("ldpc_experiment_run");
             parts[g] = from_counters(cnt, secs);
@@ -152,8 +169,8 @@ inline vector<ExperimentResult> gpu_qpadmm_grid(const vector<double> &alphas, co
         workers.emplace_back([&, g] {
             const size_t begin = points * g / gpus, end = points * (g + 1) / gpus;
             if (begin == end) return;
-            ldpc_code_t *code = CodeCache::instance().get(H, g);
-            if (ldpc_qpadmm_grid_run(code, (int32_t) (end - begin), alphas.data() + begin, mus.data() + begin, max_iter,
+            CodeRef code = CodeCache::instance().get(H, g);
+            if (ldpc_qpadmm_grid_run(code.get(), (int32_t) (end - begin), alphas.data() + begin, mus.data() + begin, max_iter,
                                      eps_stop, snr, seed, 0, frames, LDPC_CW_TABLE, words.data(), frames,
                                      cnt.data() + begin * LDPC_CNT_COUNT, &secs[g]) != LDPC_OK)
                 die("ldpc_qpadmm_grid_run");

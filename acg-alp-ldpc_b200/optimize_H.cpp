@@ -5,9 +5,14 @@
 // proposal is accepted iff its FER is strictly lower, every accepted matrix is
 // written to the save path.  Every proposal is a new H, hence a new code handle.
 //
-// Environment: LDPC_OPT_ITERS (default 10000), LDPC_OPT_SAVE (default data/optimalH.txt),
+// Environment: LDPC_OPT_ITERS (default 10000), LDPC_OPT_SAVE (default data/optimalH.txt), LDPC_OPT_WINDOW (proposals
+//              evaluated speculatively at once, default = the number of GPUs; the trajectory does not depend on it),
 //              LDPC_OPT_START (a matrix stem to start from instead of a random one).
 #include <memory>
+#include <mutex>
+#include <functional>
+#include <condition_variable>
+#include <thread>
 #include <utility>
 
 #include "experiment.h"
@@ -85,20 +90,88 @@ private:
     vector<vector<int>> _diagonals;
 };
 
+// Persistent host threads for the concurrent evaluations: worker k is pinned to GPU k % gpus and keeps its CUDA
+// stream and buffers (the library's workspaces are per host thread) for the whole search.
+class ProposalPool {
+public:
+    ProposalPool(int workers, int gpus) {
+        for (int k = 0; k < workers; ++k)
+            threads_.emplace_back([this, k, gpus] {
+                ldpc_host::pinned_gpu() = k % gpus;
+                int seen = 0;
+                for (;;) {
+                    unique_lock<mutex> lock(mu_);
+                    cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
+                    if (stop_) return;
+                    seen = generation_;
+                    const bool mine = k < count_;
+                    lock.unlock();
+                    if (mine) job_(k);
+                    lock.lock();
+                    if (mine && --pending_ == 0) done_.notify_all();
+                }
+            });
+    }
+    ~ProposalPool() {
+        { lock_guard<mutex> lock(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (thread &t : threads_) t.join();
+    }
+    // job(k) for k in [0, count) on worker k; returns when all are done
+    void run(int count, function<void(int)> job) {
+        unique_lock<mutex> lock(mu_);
+        job_ = job;
+        count_ = pending_ = count;
+        ++generation_;
+        cv_.notify_all();
+        done_.wait(lock, [&] { return pending_ == 0; });
+    }
+
+private:
+    vector<thread> threads_;
+    mutex mu_;
+    condition_variable cv_, done_;
+    function<void(int)> job_;
+    int generation_ = 0, count_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
+// The reference's chain (optimize_H.cpp:89-104), evaluated speculatively: the next `window` proposals are all drawn
+// from the CURRENT matrix with the generator states the sequential loop would have, their FERs are evaluated
+// concurrently (one host thread each, dealt round-robin to the visible GPUs), and the first improving one is
+// accepted -- the later ones are discarded and the generator is rewound to the state right after the accepted draw.
+// The accepted sequence, the printed lines and the saved matrices are those of the sequential loop (window = 1).
 template <typename Gen>
-PermutationsMatrix optimize(PermutationsMatrix H, Gen &rnd, int iters, const string &save_filepath) {
+PermutationsMatrix optimize(PermutationsMatrix H, Gen &rnd, int iters, const string &save_filepath, int window) {
     double error = FER(H.to_tmatrix());
     cout << "initial FER=" << error << endl;
-    for (int i = 0; i < iters; i++) {
-        PermutationsMatrix candidate = H.random_permute(rnd);
-        const double candidate_error = FER(candidate.to_tmatrix());
-        cout << "\tproposal: FER=" << candidate_error << endl;
-        if (candidate_error < error) {
-            H = candidate;
-            error = candidate_error;
-            cout << "accept, FER=" << error << endl;
-            save_matrix(H.to_tmatrix(), save_filepath);
+    ProposalPool pool(window > 1 ? window : 0, ldpc_host::visible_gpus());
+    for (int i = 0; i < iters;) {
+        const int w = max(1, min(window, iters - i));
+        vector<PermutationsMatrix> candidates;
+        vector<Gen> state_after;
+        Gen draw = rnd;
+        for (int k = 0; k < w; ++k) {
+            candidates.push_back(H.random_permute(draw));
+            state_after.push_back(draw);
         }
+        vector<double> errors(w, 1.0);
+        if (w == 1) errors[0] = FER(candidates[0].to_tmatrix());
+        else pool.run(w, [&](int k) { errors[k] = FER(candidates[k].to_tmatrix()); });
+        int used = w;
+        for (int k = 0; k < w; ++k) {
+            cout << "\tproposal: FER=" << errors[k] << endl;
+            if (errors[k] < error) {
+                H = candidates[k];
+                error = errors[k];
+                cout << "accept, FER=" << error << endl;
+                save_matrix(H.to_tmatrix(), save_filepath);
+                used = k + 1;
+                break;
+            }
+        }
+        rnd = state_after[used - 1];
+        i += used;
     }
     return H;
 }
@@ -128,7 +201,9 @@ int main() {
     PermutationsMatrix H0 = getenv("LDPC_OPT_START") ? PermutationsMatrix(20, load_matrix(getenv("LDPC_OPT_START")))
                                                      : random_permutation_matrix(20, 8, 14);
     mt19937 rnd(239);
-    TMatrix H = optimize(H0, rnd, iters, save).to_tmatrix();
+    // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value)
+    const int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : ldpc_host::visible_gpus();
+    TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
 
     cout << FER(H, 10000) << endl;
     return 0;
