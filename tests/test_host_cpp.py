@@ -76,3 +76,18 @@ def test_rows_files_agree_with_dense_expansion():
     ov = H.astype(np.int32) @ H.T.astype(np.int32)
     np.fill_diagonal(ov, 0)
     assert ov.max() <= 1                               # no 4-cycles
+
+
+@pytest.mark.parametrize("driver", ["main.cpp", "qpadmm_params.cpp", "optimize_H.cpp"])
+def test_drivers_compile_and_link(driver, tmp_path):
+    """the reference's three executables (Makefile:8-24) build against the C ABI library"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ldpc_build", os.path.join(PKG, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = mod.build()
+    exe = str(tmp_path / driver.replace(".cpp", ""))
+    subprocess.run(["g++", "-std=c++17", "-pthread", "-O1", "-I" + PKG, "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(PKG, driver), "-o", exe, "-L" + PKG, "-lldpc_b200",
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    assert os.path.exists(exe)
