@@ -1,8 +1,8 @@
-"""FER of the CUDA decoders against the UNMODIFIED reference (oracle/_ref, one single-threaded process per host
+"""(run on the GPU box; not collected by pytest)  FER of the CUDA decoders against the UNMODIFIED reference (oracle/_ref, one single-threaded process per host
 core -- the reference's own multi-threaded harness is racy) at every SNR of main.cpp:27, with 95 %
 binomial confidence intervals.  BASELINE.json's bar: the two FERs agree within the intervals at every SNR.
 
-    python acg-alp-ldpc_b200/tools/fer_vs_reference.py [--gpu-frames 20000] [--ref-frames-per-core 100] [--out FILE]
+    python tests/fer_vs_reference.py [--gpu-frames 20000] [--ref-frames-per-core 100] [--out FILE]
 
 GPU side: ldpc_experiment_run with codewords u*G (G = the reference's GetOrtogonal(H)) and the Philox channel.
 Reference side: the single-threaded exp() loop (experiment.h:85-121) replayed frame by frame with the reference's own
@@ -19,9 +19,8 @@ import time
 
 import numpy as np
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.dirname(HERE))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "acg-alp-ldpc_b200"))
 sys.path.insert(0, ROOT)
 from tests.helpers import load_rows  # noqa: E402
 
