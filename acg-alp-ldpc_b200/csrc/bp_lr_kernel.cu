@@ -111,9 +111,11 @@ __device__ __forceinline__ P2 operator*(P2 x, P2 y) { return P2{x.a * y.a, x.b *
 __device__ __forceinline__ P2 fma2(P2 x, P2 y, P2 z) { return P2{__fma_rn(x.a, y.a, z.a), __fma_rn(x.b, y.b, z.b)}; }
 __device__ __forceinline__ P2 div2(P2 x, P2 y) { return P2{div_pos(x.a, y.a), div_pos(x.b, y.b)}; }
 
-// clamp to [exp(-C1), exp(C1)] on the high word and put the variable's decision into the sign bit
-__device__ __forceinline__ double clamp_sign(double x, int lo, int hi, int sign) {
-    return __hiloint2double(min(max(__double2hiint(x), lo), hi) | sign, __double2loint(x));
+// clamp to [exp(-C1), exp(C1)] on the high word and put the variable's decision into the sign bit, in two integer
+// instructions: t = clamp(hi - lo, 0, range) is one VIADDMNMX.RELU, and (t + lo) | sign == t + (lo + sign) because
+// t + lo < 2^31.  neg_lo = -lo, range = hi - lo, lo_sign = lo + (decision << 31).
+__device__ __forceinline__ double clamp_sign(double x, int neg_lo, int range, int lo_sign) {
+    return __hiloint2double(__viaddmin_s32_relu(__double2hiint(x), neg_lo, range) + lo_sign, __double2loint(x));
 }
 
 // ---- variable node of degree D, two frames: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
@@ -148,10 +150,11 @@ __device__ __forceinline__ void lr_var_update(char *msg_p, const char *lch_p, ch
     }
     const P2 tot = lam[d - 1] * x[d - 1];       // posterior likelihood ratios
     const bool one_a = tot.a <= 1.0, one_b = tot.b <= 1.0;   // estimate <= 0 -> bit 1 (bp.h:193)
-    const int sa = one_a ? (int) 0x80000000 : 0, sb = one_b ? (int) 0x80000000 : 0;
+    const int sa = clamp_lo + (one_a ? (int) 0x80000000 : 0), sb = clamp_lo + (one_b ? (int) 0x80000000 : 0);
+    const int neg_lo = -clamp_lo, range = clamp_hi - clamp_lo;
 #pragma unroll
     for (int j = 0; j < d; ++j)
-        st_p2(msg_p + w[1 + j], P2{clamp_sign(lam[j].a, clamp_lo, clamp_hi, sa), clamp_sign(lam[j].b, clamp_lo, clamp_hi, sb)});
+        st_p2(msg_p + w[1 + j], P2{clamp_sign(lam[j].a, neg_lo, range, sa), clamp_sign(lam[j].b, neg_lo, range, sb)});
     *reinterpret_cast<uint16_t *>(dec_p + (w[0] >> 3)) = (uint16_t) ((one_a ? 1 : 0) | (one_b ? 0x100 : 0));
     if (SOFT) st_p2(post_p + w[0], tot);
 }
@@ -405,20 +408,37 @@ static int rec_words_of(const ldpc_code *c) {
     return words;
 }
 
-// Deals the steps (64/F consecutive node ranks of one degree class = one node per lane group) to the warps
-// round-robin, heaviest classes first, so the warps of a pass finish together.  Per warp: its steps in that
-// order, terminated by a 0 word.
+// Deals the steps (64/F consecutive node ranks of one degree class = one node per lane group) to the warps so that
+// the warps of a pass finish together: longest-processing-time first onto the least loaded warp, with the executed
+// instructions of a step as its cost (body + fixed part, profiles/r01_bp_lr_final_ncu.txt).  Per warp: its steps by
+// descending degree (the kernel runs one loop per degree), terminated by a 0 word.
 template <typename FirstOf>
-static std::vector<std::vector<uint32_t>> deal_steps(const std::vector<BpClass> &classes, int F, int nwarps, FirstOf first_of) {
+static std::vector<std::vector<uint32_t>> deal_steps(const std::vector<BpClass> &classes, int F, int nwarps, bool check_pass,
+                                                     FirstOf first_of) {
     const int G = 64 / F;
-    std::vector<int> order(classes.size());
-    for (size_t k = 0; k < classes.size(); ++k) order[k] = (int) k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return classes[a].degree > classes[b].degree; });
+    struct Step { uint32_t word; int degree, cost; };
+    std::vector<Step> all;
+    for (size_t k = 0; k < classes.size(); ++k)
+        for (int n0 = 0; n0 < classes[k].count; n0 += G) {
+            const int d = classes[k].degree;
+            all.push_back(Step{lr_step_word(first_of((int) k, n0), std::min(G, classes[k].count - n0), d), d,
+                               check_pass ? 12 + 33 * d : 32 + 18 * d});
+        }
+    std::stable_sort(all.begin(), all.end(), [](const Step &a, const Step &b) { return a.cost > b.cost; });
+    std::vector<std::vector<Step>> mine(nwarps);
+    std::vector<long> load(nwarps, 0);
+    const bool round_robin = getenv("LDPC_BP_DEAL_RR") != nullptr;     // the previous dealing, for comparison runs
+    for (size_t i = 0; i < all.size(); ++i) {
+        int w = (int) (i % nwarps);
+        if (!round_robin) w = (int) (std::min_element(load.begin(), load.end()) - load.begin());
+        mine[w].push_back(all[i]);
+        load[w] += all[i].cost;
+    }
     std::vector<std::vector<uint32_t>> per_warp(nwarps);
-    int s_global = 0;
-    for (int k : order)
-        for (int n0 = 0; n0 < classes[k].count; n0 += G, ++s_global)
-            per_warp[s_global % nwarps].push_back(lr_step_word(first_of(k, n0), std::min(G, classes[k].count - n0), classes[k].degree));
+    for (int w = 0; w < nwarps; ++w) {
+        std::stable_sort(mine[w].begin(), mine[w].end(), [](const Step &a, const Step &b) { return a.degree > b.degree; });
+        for (const Step &st : mine[w]) per_warp[w].push_back(st.word);
+    }
     return per_warp;
 }
 
@@ -628,10 +648,10 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                     F, clash_v, pairs_v, clash_c, pairs_c);
         if (rec.size() * 4 >= (1u << 18) || (size_t) n_slots * F * 8 >= (1u << 18))
             return fail(LDPC_E_UNSUPPORTED, "code too large for the 18-bit step offsets of the BP kernel");
-        auto sv = deal_steps(c->var_classes, F, nwarps, [&](int cls, int node0) {
+        auto sv = deal_steps(c->var_classes, F, nwarps, false, [&](int cls, int node0) {
             return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 16);
         });
-        auto sc = deal_steps(c->chk_classes, F, nwarps, [&](int cls, int node0) {
+        auto sc = deal_steps(c->chk_classes, F, nwarps, true, [&](int cls, int node0) {
             return (uint32_t) (class_slot0[cls] + node0 * (c->chk_classes[cls].degree | pad_even)) * F * 8;
         });
         size_t mv = 1, mc = 1;

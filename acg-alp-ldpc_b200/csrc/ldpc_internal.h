@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -77,12 +78,12 @@ struct AdmmVarRec {   // indexed by variable rank
 // tables of the check-centric QP-ADMM kernel (qpadmm_chk_kernel.cu), built on first use
 struct AdmmChkTables {
     bool built = false, supported = false;
-    uint32_t *chk_tab = nullptr, *var_words = nullptr;
-    uint4 *var_inc = nullptr;
+    uint32_t *chk_tab = nullptr, *var_stream = nullptr;
     uint16_t *var_rank = nullptr, *var_e = nullptr;
     uint32_t plane_base[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int special_lo = 0, special_hi = 0;
     int n_chk = 0, n_chunks = 0, n_inc = 0, n_slots = 0, tab_stride = 0, max_nb = 0, e_min = 0;
+    int stream_rows = 0;          // rows of var_stream (words per lane column, two rows of padding included)
 };
 
 struct DeviceTables {
@@ -155,6 +156,7 @@ int launch_bp_log(const ldpc_code *code, const FrameIO &io, int64_t frames, doub
                   int early_exit, unsigned long long *queue, cudaStream_t stream);
 double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
 int bp_lr_layout_stats(const ldpc_code *code, int F, int32_t out[6]);
+extern std::atomic<int> g_last_qpadmm_kernel;    // 1 check-centric, 2 block-per-lane (testing hook)
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
 // the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 3..8) and block-per-lane (any code)

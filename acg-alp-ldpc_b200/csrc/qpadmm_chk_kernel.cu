@@ -14,6 +14,10 @@
 //     v          the variable values (two buffers, see below), written by the variable lanes, gathered by the
 //                check lanes in ascending variable order (qp_admm.h:144-151)
 //     qa, inv    q_i + alpha/2 and -1/(mu e_i - alpha)
+// The variable phase of a lane is a static stream of one 32-bit word per incidence (chunk offset, sign flips, end
+// of variable / end of column), software-pipelined one incidence ahead: its dependent chain is the reference's
+// own chain of additions and nothing else (profiles/r01_admm_chk_sweep.txt: 140.7 -> 132.4 ms against per-slot
+// records that were looked up on the way).
 // Compared with the block-per-lane kernel this drops the auxiliary variables' round trip (half of all gathers),
 // all per-iteration table loads of the check phase (the lane <-> check mapping is static) and the sign-flip
 // arithmetic of the residuals and of the auxiliary updates (signs are static there).
@@ -30,6 +34,7 @@
 //   barrier
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -45,15 +50,15 @@ constexpr uint32_t CHK_EMPTY_SLOT = 0xffffffffu;
 struct AdmmChkParams {
     KernelIO io;
     const uint32_t *chk_tab;      // per check rank: tab_stride words: degree, then the STORAGE SLOTS of its variables (ascending variable index)
-    const uint32_t *var_words;    // per variable slot: (offset of its incidence records) << 10 | e << 4 | incidences, or CHK_EMPTY_SLOT
-    const uint4 *var_inc;         // incidence records {chunk index, flip mask w0, flip mask w1, flip mask w2}, row order
     const uint16_t *var_slot;     // variable index -> storage slot
     const uint16_t *slot_e;       // per slot: sum of squared coefficients of the variable's column (qp_admm.h:94-99)
+    const uint32_t *var_stream;   // variable phase as one word per incidence and lane column (see chk_stream_word)
+    int stream_rows;              // words per lane column (row k of column c at index k * columns + c)
     uint32_t plane_base[CHK_MAX_NB];   // chunk index of check rank 0's k-th block
-    int n_chk, n_slots, n_chunks, n_inc, tab_stride;
+    int n_chk, n_slots, n_chunks, tab_stride;
     int special_lo, special_hi;   // chunks [lo, hi) belong to one- and two-variable checks (no row with b = 2)
     // byte offsets of the arrays in dynamic shared memory
-    uint32_t off_w23, off_v, off_qa, off_inv, off_red, off_inc, off_vw, off_cw, off_ctl;
+    uint32_t off_w23, off_v, off_qa, off_inv, off_red, off_str, off_cw, off_ctl;
     int max_iter;
     double alpha, mu, eps_stop;
     int chunk;                    // frames claimed from the global queue at a time
@@ -62,6 +67,18 @@ struct AdmmChkParams {
     const double *grid_alpha, *grid_mu;
     long long grid_frames;
 };
+
+// Variable phase as a stream: the incidences of the variables of one lane column (slots c, c + columns, ...) back to
+// back, one word each, in the reference's gather order (ascending row, qp_admm.h:133-138):
+//   bits 4-19   byte offset of the block's chunk in w01 (w23: + off_w23)
+//   bits 20-25  e of the variable (sum of squared coefficients of its column; grid mode looks inv_coef up by it)
+//   bits 31/30/29  flip the sign of the row term 0 / 1 / 2 (coefficient -1)
+//   bit 1 FIRST  first word of a variable (informative: the kernel loads q + alpha/2 of the next variable at LAST)
+//   bit 0 LAST   last word of a variable: scale, clip, store v, move on to the column's next slot
+//   bit 2 NOADD  no row terms (a variable without edges, or a column without variables): the offset is that of the
+//                all-zero chunk behind the last real one
+//   bit 3 END    last word of the column
+constexpr uint32_t STR_LAST = 1u, STR_FIRST = 2u, STR_NOADD = 4u, STR_END = 8u, STR_OFF_MASK = 0xffff0u;
 
 struct ChkCtl {
     unsigned live;                // slots holding a frame
@@ -180,12 +197,12 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     slots_init(S);
     for (int r = tid; r < p.n_slots; r += nt) {
         reinterpret_cast<double *>(sm + p.off_inv)[r] = inv_coef(p.mu, p.alpha, (double) p.slot_e[r]);
-        reinterpret_cast<uint32_t *>(sm + p.off_vw)[r] = p.var_words[r];
     }
-    for (int a = tid; a < p.n_inc; a += nt) {
-        uint4 rec = p.var_inc[a];
-        rec.x = rec.x * (F * 16);                     // chunk index -> byte offset
-        reinterpret_cast<uint4 *>(sm + p.off_inc)[a] = rec;
+    for (int a = tid; a < p.stream_rows * (nt / F); a += nt)
+        reinterpret_cast<uint32_t *>(sm + p.off_str)[a] = p.var_stream[a];
+    if (tid < F) {                                        // the all-zero chunk
+        sts_f64x2(sbase + (p.n_chunks * F + tid) * 16, 0.0, 0.0);
+        sts_f64x2(sbase + p.off_w23 + (p.n_chunks * F + tid) * 16, 0.0, 0.0);
     }
     if (tid == 0) {
         L->c.live = L->c.ran = L->c.done[0] = L->c.done[1] = L->c.fresh = 0u;
@@ -223,8 +240,9 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     const uint32_t a_v0 = sbase + p.off_v + f * 8;                  // + slot * F * 8   (second buffer: + vbuf)
     const uint32_t vbuf = (uint32_t) p.n_slots * F * 8;
     const uint32_t a_qa = sbase + p.off_qa + f * 8;
-    const uint32_t a_inv = sbase + p.off_inv, a_inc = sbase + p.off_inc, a_vw = sbase + p.off_vw;
+    const uint32_t a_inv = sbase + p.off_inv;
     const uint32_t a_invtab = smem_addr(&L->inv_tab[0][0]) + f * 8;
+    const uint32_t a_str = sbase + p.off_str + cr * 4;
     __syncthreads();
 
     for (unsigned trip = 0;; ++trip) {
@@ -248,25 +266,51 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
         if (tid == 0) L->c.fresh = 0u;    // everybody read it before the last barrier; the refill below sets it again
 
         // ---- variable phase, qp_admm.h:132-142: this lane's column of variable slots
-        // (prefetching the next incidence's records and row terms costs more in registers than it hides: 153 vs 141 ms)
         if ((live >> f) & 1u) {
-            for (int slot = cr; slot < p.n_slots; slot += cpt) {
-                const uint32_t word = lds_u32(a_vw + slot * 4);
-                if (word == CHK_EMPTY_SLOT) continue;
-                uint32_t rec = a_inc + (word >> 10) * 16;
-                const uint32_t rec_end = rec + (word & 15u) * 16;
-                double B = lds_f64(a_qa + slot * (F * 8));
-                for (; rec != rec_end; rec += 16) {
-                    const uint4 r = lds_u32x4(rec);
-                    const double2 a01 = lds_f64x2(a_w01 + r.x), a23 = lds_f64x2(a_w01 + p.off_w23 + r.x);
-                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.x) ^ (int) r.y, __double2loint(a01.x)));
-                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a01.y) ^ (int) r.z, __double2loint(a01.y)));
-                    B = __dadd_rn(B, __hiloint2double(__double2hiint(a23.x) ^ (int) r.w, __double2loint(a23.x)));
-                    B = __dadd_rn(B, a23.y);
-                }
-                const double ic = GRID ? lds_f64(a_invtab + ((word >> 4) & 63u) * (F * 8)) : lds_f64(a_inv + slot * 8);
-                sts_f64(a_vcur + slot * (F * 8), clip01_int(__dmul_rn(B, ic)));
+            // One word per incidence.  The row terms of the next incidence and the word after it are in flight while the
+            // four additions of this one retire; two steps per trip of the loop so that the row-term registers alternate
+            // instead of being copied.  B always holds q + alpha/2 of the variable about to start (loaded when its
+            // predecessor is stored), so a variable needs no "first" test.
+            // (Two interleaved streams per lane -- two addition chains -- change nothing, 330.6 vs 331.0 ms on the
+            // (3,6)-1008 code: with the loads in flight early the phase is bound by shared-memory wavefronts.)
+            const uint32_t a_w23 = a_w01 + p.off_w23;
+            const uint32_t s_str = (uint32_t) cpt * 4, s_slot = (uint32_t) cpt * (F * 8), s_inv = (uint32_t) cpt * 8;
+#define LDPC_VAR_STEP(W, A01, A23, B, AQ, AV, AI)                                                                  \
+    B = __dadd_rn(B, flip_by(A01.x, W));                                                                           \
+    B = __dadd_rn(B, flip_by(A01.y, W << 1));                                                                      \
+    B = __dadd_rn(B, flip_by(A23.x, W << 2));                                                                      \
+    B = __dadd_rn(B, A23.y);                                                                                       \
+    if (W & STR_LAST) {                                                                                            \
+        const double ic = GRID ? lds_f64(a_invtab + ((W >> 20) & 63u) * (F * 8)) : lds_f64(AI);                    \
+        AQ += s_slot;                                                                                              \
+        const double vnew = clip01_int(__dmul_rn(B, ic));                                                          \
+        B = lds_f64(AQ);                                                                                           \
+        sts_f64(AV, vnew);                                                                                         \
+        AV += s_slot;                                                                                              \
+        AI += s_inv;                                                                                               \
+    }
+            uint32_t a_s = a_str, a_q = a_qa + cr * (F * 8), a_vv = a_vcur + cr * (F * 8), a_i = a_inv + cr * 8;
+            uint32_t w = lds_u32(a_s);
+            double2 a01 = lds_f64x2(a_w01 + (w & STR_OFF_MASK)), a23 = lds_f64x2(a_w23 + (w & STR_OFF_MASK));
+            double B = lds_f64(a_q);
+            a_s += s_str;
+            uint32_t wn = lds_u32(a_s);
+            for (;;) {
+                const double2 n01 = lds_f64x2(a_w01 + (wn & STR_OFF_MASK)), n23 = lds_f64x2(a_w23 + (wn & STR_OFF_MASK));
+                a_s += s_str;
+                const uint32_t wnn = lds_u32(a_s);
+                LDPC_VAR_STEP(w, a01, a23, B, a_q, a_vv, a_i)
+                if (w & STR_END) break;
+                a01 = lds_f64x2(a_w01 + (wnn & STR_OFF_MASK));
+                a23 = lds_f64x2(a_w23 + (wnn & STR_OFF_MASK));
+                a_s += s_str;
+                w = lds_u32(a_s);
+                LDPC_VAR_STEP(wn, n01, n23, B, a_q, a_vv, a_i)
+                if (wn & STR_END) break;
+                wn = w;
+                w = wnn;
             }
+#undef LDPC_VAR_STEP
         }
         __syncthreads();
 
@@ -434,6 +478,150 @@ static int upload_chk(T **dst, const std::vector<T> &src) {
     return LDPC_OK;
 }
 
+// Bank-aware ranks for codes that run one frame per CTA (more than 320 live checks): with F = 1 a warp's gathers go to
+// 32 unrelated addresses -- 43 % of all shared-memory wavefronts of the (3,6)-1008 code were replays
+// (profiles/r01b_admm_chk_1008_ncu.txt).  The order of the checks inside a degree class and of the variables inside
+// a degree class is free (warps stay uniform, the columns stay balanced, the arithmetic does not change), so a
+// deterministic annealing pass picks both to spread every warp-wide gather over the banks:
+//   v gather of the check phase   G = 32/F consecutive check ranks read, for position j, the slots of their j-th
+//                                 variables: F x 8 bytes each, 16/F positions per 128-byte wavefront
+//   w gather of the variable phase  G consecutive lane columns read, at row k of their streams, one chunk each:
+//                                 F x 16 bytes, 8/F positions per wavefront
+// Cost of an access = wavefronts beyond the minimum for its number of active lanes.
+static void chk_anneal(const ldpc_code *c, int F, int cols, const uint32_t *plane_base, std::vector<int> &chk,
+                       std::vector<int> &var) {
+    const int n = c->n, m = (int) chk.size(), G = 32 / F, bins_a = 16 / F, bins_c = 8 / F;
+    const int steps = (n + cols - 1) / cols;
+    auto cdeg = [&](int r) { return c->row_ptr[r + 1] - c->row_ptr[r]; };
+    auto vdeg = [&](int v) { return c->col_ptr[v + 1] - c->col_ptr[v]; };
+    std::vector<int> edge_chk(c->E), edge_plane(c->E);
+    int maxdeg = 0;
+    for (int r = 0; r < c->m; ++r) {
+        const int d = cdeg(r);
+        maxdeg = std::max(maxdeg, d);
+        for (int j = 0; j < d; ++j) {
+            edge_chk[c->row_ptr[r] + j] = r;
+            edge_plane[c->row_ptr[r] + j] = d >= 3 ? (j == 0 ? 0 : (j == d - 1 ? d - 3 : j - 1)) : 0;
+        }
+    }
+    std::vector<int> rank_of_chk(c->m, -1), pos_of_var(n);
+    for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
+    for (int i = 0; i < n; ++i) pos_of_var[var[i]] = i;
+    auto col_of_pos = [&](int i) { const int j = i / cols, k = i % cols; return (j & 1) ? cols - 1 - k : k; };
+    auto slot_of_pos = [&](int i) { return (i / cols) * cols + col_of_pos(i); };
+    auto cost_a = [&](int g) {
+        int cost = 0;
+        const int r1 = std::min(m, g * G + G);
+        for (int j = 0; j < maxdeg; ++j) {
+            int cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, act = 0, worst = 0;
+            for (int i = g * G; i < r1; ++i) {
+                const int r = chk[i];
+                if (j >= cdeg(r)) continue;
+                ++act;
+                worst = std::max(worst, ++cnt[slot_of_pos(pos_of_var[c->col_idx[c->row_ptr[r] + j]]) % bins_a]);
+            }
+            if (act) cost += worst - (act + bins_a - 1) / bins_a;
+        }
+        return cost;
+    };
+    std::vector<int> chunks;                         // scratch: [column in warp][row] -> chunk, -1 beyond the end
+    auto cost_c = [&](int h) {
+        const int c1 = std::min(cols, h * G + G), width = c1 - h * G;
+        int rows = 0;
+        chunks.assign((size_t) G * 16 * steps, -1);
+        const int cap = 16 * steps;
+        for (int col = h * G; col < c1; ++col) {
+            int k = 0;
+            for (int j = 0; j < steps; ++j) {
+                const int i = j * cols + ((j & 1) ? cols - 1 - col : col);
+                if (i >= n) continue;
+                const int v = var[i];
+                for (int q = c->col_ptr[v]; q < c->col_ptr[v + 1] && k < cap; ++q, ++k) {
+                    const int e = c->csc_edge[q];
+                    chunks[(size_t) (col - h * G) * cap + k] = (int) plane_base[edge_plane[e]] + rank_of_chk[edge_chk[e]];
+                }
+            }
+            rows = std::max(rows, k);
+        }
+        int cost = 0;
+        for (int k = 0; k < rows; ++k) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, act = 0, worst = 0;
+            for (int x = 0; x < width; ++x) {
+                const int q = chunks[(size_t) x * cap + k];
+                if (q < 0) continue;
+                ++act;
+                worst = std::max(worst, ++cnt[q % bins_c]);
+            }
+            if (act) cost += worst - (act + bins_c - 1) / bins_c;
+        }
+        return 2 * cost;                             // two 16-byte loads (w01, w23) per stream word
+    };
+    // class ranges (equal degree) by position
+    std::vector<int> c_lo(m), c_hi(m), v_lo(n), v_hi(n);
+    for (int i = 0, s0 = 0; i <= m; ++i)
+        if (i == m || cdeg(chk[i]) != cdeg(chk[s0])) { for (int k = s0; k < i; ++k) { c_lo[k] = s0; c_hi[k] = i; } s0 = i; }
+    for (int i = 0, s0 = 0; i <= n; ++i)
+        if (i == n || vdeg(var[i]) != vdeg(var[s0])) { for (int k = s0; k < i; ++k) { v_lo[k] = s0; v_hi[k] = i; } s0 = i; }
+    uint64_t rs = 0x9E3779B97F4A7C15ull;             // xorshift: the layout must not depend on the C++ library
+    auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t) (rs >> 11); };
+    const int moves = 40 * (n + m);
+    std::vector<int> ga, gc;
+    auto replays = [&]() {
+        long t = 0;
+        for (int g = 0; g * G < m; ++g) t += cost_a(g);
+        for (int h = 0; h * G < cols; ++h) t += cost_c(h);
+        return t;
+    };
+    const bool stats = getenv("LDPC_ADMM_LAYOUT_STATS") != nullptr;
+    const long replays_before = replays();
+    long now = replays_before, best = replays_before;
+    std::vector<int> best_chk(chk), best_var(var);
+    for (int it = 0; it < moves; ++it) {
+        const double temp = 0.6 * std::pow(0.02, (double) it / moves);
+        ga.clear(); gc.clear();
+        const bool swap_chk = (rnd() & 1u) != 0;
+        int a, b;
+        if (swap_chk) {
+            a = (int) (rnd() % (uint32_t) m);
+            b = c_lo[a] + (int) (rnd() % (uint32_t) (c_hi[a] - c_lo[a]));
+            if (a == b) continue;
+            ga = {a / G, b / G};
+            for (int x : {chk[a], chk[b]})
+                for (int e = c->row_ptr[x]; e < c->row_ptr[x + 1]; ++e) gc.push_back(col_of_pos(pos_of_var[c->col_idx[e]]) / G);
+        } else {
+            a = (int) (rnd() % (uint32_t) n);
+            b = v_lo[a] + (int) (rnd() % (uint32_t) (v_hi[a] - v_lo[a]));
+            if (a == b) continue;
+            gc = {col_of_pos(a) / G, col_of_pos(b) / G};
+            for (int x : {var[a], var[b]})
+                for (int q = c->col_ptr[x]; q < c->col_ptr[x + 1]; ++q) ga.push_back(rank_of_chk[edge_chk[c->csc_edge[q]]] / G);
+        }
+        uniq(ga); uniq(gc);
+        auto total = [&]() { int t = 0; for (int g : ga) t += cost_a(g); for (int h : gc) t += cost_c(h); return t; };
+        auto apply = [&]() {
+            if (swap_chk) { std::swap(chk[a], chk[b]); rank_of_chk[chk[a]] = a; rank_of_chk[chk[b]] = b; }
+            else { std::swap(var[a], var[b]); pos_of_var[var[a]] = a; pos_of_var[var[b]] = b; }
+        };
+        const int before = total();
+        apply();
+        const int delta = total() - before;
+        if (delta > 0 && (rnd() & 0xffffff) / 16777216.0 >= std::exp(-delta / temp)) {
+            apply();                                     // rejected: swap back
+        } else {
+            now += delta;
+            if (now < best) { best = now; best_chk = chk; best_var = var; }
+        }
+    }
+    chk = best_chk;                                      // the best state seen (the start if nothing beat it)
+    var = best_var;
+    for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
+    for (int i = 0; i < n; ++i) pos_of_var[var[i]] = i;
+    if (stats)
+        fprintf(stderr, "admm check-kernel layout F=%d: %ld -> %ld replayed wavefronts per iteration (%d moves)\n", F,
+                replays_before, replays(), moves);
+}
+
+
 static int live_checks(const ldpc_code *c) {
     int k = 0;
     for (int r = 0; r < c->m; ++r) k += c->row_ptr[r + 1] > c->row_ptr[r];
@@ -472,23 +660,9 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
             for (int i = 0; i < n; ++i) var[i] = i;
             std::stable_sort(chk.begin(), chk.end(), [&](int a, int b) { return cdeg(a) > cdeg(b); });
             std::stable_sort(var.begin(), var.end(), [&](int a, int b) { return vdeg(a) > vdeg(b); });
-            for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
             t.n_chk = m;
             t.max_nb = std::max(1, cdeg(chk[0]) - 2);
-            // Variable slots: lane column c of the CTA updates the slots c, c + cols, c + 2 cols, ...  The variables
-            // are dealt to the columns in boustrophedon order, heaviest first, so that every column gets about the
-            // same number of incidences (the variable phase ends at a barrier) and neighbouring columns -- the lanes
-            // of one warp -- get variables of equal degree.
             const int cols = chk_threads(c, F) / F;
-            const int steps = (n + cols - 1) / cols;
-            t.n_slots = steps * cols;
-            std::vector<int> slot_of_var(n, 0), var_of_slot(t.n_slots, -1);
-            for (int i = 0; i < n; ++i) {
-                const int j = i / cols, k = i % cols;
-                const int col = (j & 1) ? cols - 1 - k : k;
-                slot_of_var[var[i]] = j * cols + col;
-                var_of_slot[j * cols + col] = var[i];
-            }
             // block k of every check that has one: a plane of consecutive chunks indexed by check rank
             int base = 0;
             for (int k = 0; k < CHK_MAX_NB; ++k) {
@@ -498,6 +672,24 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
                 base += (cnt + 1) & ~1;            // even bases: neighbouring checks write neighbouring rows
             }
             t.n_chunks = base;
+            // codes too large for two frames per CTA run one CTA per SM, bound by shared-memory wavefronts: bank-aware ranks
+            bool anneal = F == 1 && chk_threads(c, 2) > 640;
+            if (const char *force = getenv("LDPC_ADMM_ANNEAL")) anneal = atoi(force) != 0;
+            if (anneal) chk_anneal(c, F, cols, t.plane_base, chk, var);
+            for (int i = 0; i < m; ++i) rank_of_chk[chk[i]] = i;
+            // Variable slots: lane column c of the CTA updates the slots c, c + cols, c + 2 cols, ...  The variables
+            // are dealt to the columns in boustrophedon order, heaviest first, so that every column gets about the
+            // same number of incidences (the variable phase ends at a barrier) and neighbouring columns -- the lanes
+            // of one warp -- get variables of equal degree.
+            const int steps = (n + cols - 1) / cols;
+            t.n_slots = steps * cols;
+            std::vector<int> slot_of_var(n, 0), var_of_slot(t.n_slots, -1);
+            for (int i = 0; i < n; ++i) {
+                const int j = i / cols, k = i % cols;
+                const int col = (j & 1) ? cols - 1 - k : k;
+                slot_of_var[var[i]] = j * cols + col;
+                var_of_slot[j * cols + col] = var[i];
+            }
             {   // the one- and two-variable checks are the last ranks (degree descending): their chunks in plane 0
                 int m3 = 0;
                 for (int i = 0; i < m; ++i) m3 += cdeg(chk[i]) >= 3;
@@ -553,11 +745,39 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
             }
             if (inc.size() >= (1u << 22)) t.supported = false;
             t.n_inc = (int) inc.size();
+            // the same incidences as a stream per lane column (chk_stream_word): column c owns the slots c, c + cols, ...
+            if ((size_t) (t.n_chunks + 1) * F * 16 > STR_OFF_MASK) t.supported = false;
+            const uint32_t zero_off = (uint32_t) t.n_chunks * (uint32_t) (F * 16);   // a chunk of zeros behind the last one: NOADD words add it
+            std::vector<std::vector<uint32_t>> col_words(cols);
+            for (int col = 0; col < cols; ++col) {
+                std::vector<uint32_t> &cwds = col_words[col];
+                for (int j = 0; j < steps; ++j) {
+                    const int sl = j * cols + col;
+                    if (var_of_slot[sl] < 0) continue;           // only in the last row: nothing follows in this column
+                    const uint32_t first = words[sl] >> 10, cnt = words[sl] & 15u, e = (words[sl] >> 4) & 63u;
+                    if (cnt == 0) cwds.push_back(STR_FIRST | STR_LAST | STR_NOADD | (e << 20) | zero_off);
+                    for (uint32_t q = 0; q < cnt; ++q) {
+                        const uint4 &rec = inc[first + q];
+                        uint32_t wd = (rec.x * (uint32_t) (F * 16)) | (e << 20);
+                        wd |= (rec.y & 0x80000000u) | ((rec.z & 0x80000000u) >> 1) | ((rec.w & 0x80000000u) >> 2);
+                        if (q == 0) wd |= STR_FIRST;
+                        if (q + 1 == cnt) wd |= STR_LAST;
+                        cwds.push_back(wd);
+                    }
+                }
+                if (cwds.empty()) cwds.push_back(STR_NOADD | zero_off);
+                cwds.back() |= STR_END;
+            }
+            size_t kmax = 0;
+            for (const auto &cwds : col_words) kmax = std::max(kmax, cwds.size());
+            t.stream_rows = (int) kmax + 2;                  // the kernel reads up to two words past a column's end
+            std::vector<uint32_t> stream((size_t) t.stream_rows * cols, STR_NOADD | STR_END | zero_off);
+            for (int col = 0; col < cols; ++col)
+                for (size_t k = 0; k < col_words[col].size(); ++k) stream[k * cols + col] = col_words[col][k];
             t.e_min = e_min;
             int st;
             if ((st = upload_chk(&t.chk_tab, tab))) return st;
-            if ((st = upload_chk(&t.var_words, words))) return st;
-            if ((st = upload_chk(&t.var_inc, inc))) return st;
+            if ((st = upload_chk(&t.var_stream, stream))) return st;
             if ((st = upload_chk(&t.var_rank, vslot))) return st;
             if ((st = upload_chk(&t.var_e, se))) return st;
         }
@@ -571,20 +791,19 @@ static size_t up16(size_t x) { return (x + 15) & ~(size_t) 15; }
 // carve-up of the dynamic shared memory; returns the total
 static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment, AdmmChkParams *p) {
     size_t off = 0;
-    off += (size_t) t.n_chunks * F * 16;                 // w01
-    const size_t off_w23 = off; off += (size_t) t.n_chunks * F * 16;
+    off += (size_t) (t.n_chunks + 1) * F * 16;           // w01 (+ the all-zero chunk)
+    const size_t off_w23 = off; off += (size_t) (t.n_chunks + 1) * F * 16;
     const size_t off_v = off; off += (size_t) 2 * t.n_slots * F * 8;
     const size_t off_qa = off; off += (size_t) t.n_slots * F * 8;
     const size_t off_inv = off; off += (size_t) t.n_slots * 8;
     const size_t off_red = off; off += (size_t) F * 32 * 8;
-    const size_t off_inc = up16(off); off = off_inc + (size_t) t.n_inc * 16;
-    const size_t off_vw = off; off += (size_t) t.n_slots * 4;
+    const size_t off_str = off; off += (size_t) t.stream_rows * (chk_threads(c, F) / F) * 4;
     const size_t off_cw = off; off += experiment ? (size_t) F * c->n : 0;
     const size_t off_ctl = up16(off); off = off_ctl + sizeof(ChkShared<4>);
     if (p) {
         p->off_w23 = (uint32_t) off_w23; p->off_v = (uint32_t) off_v; p->off_qa = (uint32_t) off_qa;
-        p->off_inv = (uint32_t) off_inv; p->off_red = (uint32_t) off_red; p->off_inc = (uint32_t) off_inc;
-        p->off_vw = (uint32_t) off_vw; p->off_cw = (uint32_t) off_cw; p->off_ctl = (uint32_t) off_ctl;
+        p->off_inv = (uint32_t) off_inv; p->off_red = (uint32_t) off_red;
+        p->off_str = (uint32_t) off_str; p->off_cw = (uint32_t) off_cw; p->off_ctl = (uint32_t) off_ctl;
     }
     return off + 16;
 }
@@ -647,15 +866,17 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
     io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);     // grid mode: frames = work items
     io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
-    p.chk_tab = t->chk_tab; p.var_words = t->var_words; p.var_inc = t->var_inc; p.var_slot = t->var_rank;
+    p.chk_tab = t->chk_tab; p.var_slot = t->var_rank;
     p.slot_e = t->var_e;
     for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
     p.special_lo = t->special_lo; p.special_hi = t->special_hi;
-    p.n_chk = t->n_chk; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.n_inc = t->n_inc; p.tab_stride = t->tab_stride;
+    p.n_chk = t->n_chk; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.tab_stride = t->tab_stride;
     p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
     p.grid_alpha = grid_alpha; p.grid_mu = grid_mu; p.grid_frames = frames_per_point;
     const int threads = chk_threads(c, F);
     const size_t smem = chk_smem_layout(c, *t, F, exp_mode, &p);
+    p.var_stream = t->var_stream;
+    p.stream_rows = t->stream_rows;
     ChkKernel fn = chk_kernel_for(F, t->max_nb, grid);
     LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
@@ -672,7 +893,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
 
 void free_chk_tables(ldpc_code *c) {
     for (AdmmChkTables &t : c->admm_chk) {
-        cudaFree(t.chk_tab); cudaFree(t.var_words); cudaFree(t.var_inc); cudaFree(t.var_rank); cudaFree(t.var_e);
+        cudaFree(t.chk_tab); cudaFree(t.var_stream); cudaFree(t.var_rank); cudaFree(t.var_e);
     }
 }
 

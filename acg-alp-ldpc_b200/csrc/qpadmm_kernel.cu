@@ -24,6 +24,7 @@
 // move the exit by one iteration only if sum2 lands within an ulp-scale band around
 // eps_stop.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "admm_rows.cuh"
@@ -329,14 +330,21 @@ static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int 
 
 // Decoder::decode / exp() for QP-ADMM: the check-centric kernel where it applies (all checks of degree 3..8, a
 // feasible (alpha, mu)), else the block-per-lane kernel below; LDPC_ADMM_KERNEL=block|check overrides (A/B runs).
+// which kernel served the last QP-ADMM launch of this process (ldpc_debug_last_qpadmm_kernel): 1 check-centric, 2 block-per-lane
+std::atomic<int> g_last_qpadmm_kernel{0};
+
 int launch_qpadmm(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
                   int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream) {
     bool chk = true;
     if (const char *k = getenv("LDPC_ADMM_KERNEL")) chk = k[0] != 'b';
     if (chk) {
         const int st = launch_qpadmm_chk(c, fio, frames, var, alpha, mu, max_iter, eps_stop, queue, stream);
-        if (st != LDPC_E_UNSUPPORTED) return st;
+        if (st != LDPC_E_UNSUPPORTED) {
+            g_last_qpadmm_kernel = 1;
+            return st;
+        }
     }
+    g_last_qpadmm_kernel = 2;
     return launch_qpadmm_blk(c, fio, frames, var, alpha, mu, max_iter, eps_stop, queue, stream);
 }
 

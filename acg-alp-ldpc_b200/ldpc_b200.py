@@ -76,6 +76,7 @@ def lib():
     L.ldpc_measure_smem_peak.argtypes = [C.c_int, C.POINTER(dbl)]
     L.ldpc_debug_bpmath.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
     L.ldpc_debug_bp_layout.argtypes = [vp, i32, vp]
+    L.ldpc_debug_last_qpadmm_kernel.argtypes = []
     _lib = L
     return L
 
@@ -109,6 +110,11 @@ def debug_bpmath(a, ev, od, device=0):
     _check(lib().ldpc_debug_bpmath(device, a.size, a.ctypes.data, ev.ctypes.data, od.ctypes.data, out_exp.ctypes.data,
                                    out_log.ctypes.data))
     return out_exp, out_log
+
+
+def last_qpadmm_kernel():
+    """1: the check-centric kernel served the last QP-ADMM launch, 2: the block-per-lane kernel, 0: none yet"""
+    return int(lib().ldpc_debug_last_qpadmm_kernel())
 
 
 def _ptr(a):

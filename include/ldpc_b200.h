@@ -203,6 +203,11 @@ int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *
  * check pass}.  With 8 frames per CTA a shared half line is a replayed shared-memory wavefront. */
 int ldpc_debug_bp_layout(const ldpc_code_t *code, int32_t frames_per_cta, int32_t out[6]);
 
+/* ---- testing hook: which kernel served the last QP-ADMM launch of this process (decode or experiment mode):
+ * 1 = check-centric (qpadmm_chk_kernel.cu), 2 = block-per-lane (qpadmm_kernel.cu), 0 = none yet.  The parity tests
+ * assert it, so a silent fall-back to the slower kernel fails them. */
+int ldpc_debug_last_qpadmm_kernel(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ def test_qpadmm_bit_exact(codes, oracle, name, snrs, frames, max_iter):
     for snr in snrs:
         y = code.channel(SEED, 1000, frames, snr)
         gb, gok, git, gv = code.qpadmm_decode(y, snr, alpha, mu, max_iter, 1e-5)
+        # every code of BASELINE.json is inside the check-centric kernel's range: a silent fall-back is a failure
+        assert _lib(codes).last_qpadmm_kernel() == 1, "the block-per-lane kernel served %s" % name
         ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, max_iter, 1e-5)
         bad = np.flatnonzero((gb != ob).any(1) | (git != oit) | (gok != ook))
         for f in bad:
@@ -406,5 +408,6 @@ def test_qpadmm_block_kernel_fallback(codes, oracle, monkeypatch):
         alpha, mu = ADMM[name]
         y = code.channel(SEED, 9000, frames, snr)
         gb, gok, git, gv = code.qpadmm_decode(y, snr, alpha, mu, iters, 1e-5)
+        assert _lib(codes).last_qpadmm_kernel() == 2
         ob, ook, oit, ov = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, iters, 1e-5)
         assert (git == oit).all() and (gb == ob).all() and (gok == ook).all() and (gv == ov).all(), name
