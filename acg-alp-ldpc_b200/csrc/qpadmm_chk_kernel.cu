@@ -566,6 +566,7 @@ static void chk_anneal(const ldpc_code *c, int F, int cols, const uint32_t *plan
     auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t) (rs >> 11); };
     const int moves = 40 * (n + m);
     std::vector<int> ga, gc;
+    auto uniq = [](std::vector<int> &x) { std::sort(x.begin(), x.end()); x.erase(std::unique(x.begin(), x.end()), x.end()); };
     auto replays = [&]() {
         long t = 0;
         for (int g = 0; g * G < m; ++g) t += cost_a(g);
