@@ -392,6 +392,8 @@ int ldpc_debug_bpmath(int device, int32_t count, const double *a, const double *
     return debug_bpmath(device, count, a, ev, od, out_exp, out_log);
 }
 
+int ldpc_debug_last_bp_kernel(void) { return ldpc::g_last_bp_kernel.load(); }
+
 int ldpc_debug_last_qpadmm_kernel(void) { return ldpc::g_last_qpadmm_kernel.load(); }
 
 int ldpc_debug_bp_layout(const ldpc_code_t *c, int32_t frames_per_cta, int32_t out[6]) {

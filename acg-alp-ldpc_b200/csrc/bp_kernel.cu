@@ -36,6 +36,7 @@
 // reference computes; per frame agreement with it is checked in tests/.
 // Magnitudes are capped near 700 (bpmath.cuh) instead of saturating to infinity.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "bpmath.cuh"
@@ -324,6 +325,9 @@ static int launch_bp_f(BpParams &p, const ldpc_code *c, int threads, int64_t fra
 
 // Decoder::decode / exp() for BP: the likelihood-ratio kernel unless the node degrees would force its message
 // cap below 50 (the reference's own saturation point is ~45.7); LDPC_BP_KERNEL=log|lr overrides (A/B runs).
+// which kernel served the last BP launch of this process (ldpc_debug_last_bp_kernel): 1 likelihood-ratio, 2 log-domain
+std::atomic<int> g_last_bp_kernel{0};
+
 int launch_bp(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
               unsigned long long *queue, cudaStream_t stream) {
     bool lr = bp_lr_cap(c, nullptr) >= 50.0;
@@ -333,8 +337,12 @@ int launch_bp(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var
     }
     if (lr) {
         const int st = launch_bp_lr(c, fio, frames, var, max_iter, early_exit, queue, stream);
-        if (st != LDPC_E_UNSUPPORTED) return st;      // codes beyond its shared-memory layout take the log-domain kernel
+        if (st != LDPC_E_UNSUPPORTED) {               // codes beyond its shared-memory layout take the log-domain kernel
+            g_last_bp_kernel = 1;
+            return st;
+        }
     }
+    g_last_bp_kernel = 2;
     return launch_bp_log(c, fio, frames, var, max_iter, early_exit, queue, stream);
 }
 

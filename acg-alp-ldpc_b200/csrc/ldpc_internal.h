@@ -156,6 +156,7 @@ int launch_bp_log(const ldpc_code *code, const FrameIO &io, int64_t frames, doub
                   int early_exit, unsigned long long *queue, cudaStream_t stream);
 double bp_lr_cap(const ldpc_code *code, double *llr_cap_out);
 int bp_lr_layout_stats(const ldpc_code *code, int F, int32_t out[6]);
+extern std::atomic<int> g_last_bp_kernel;        // 1 likelihood-ratio, 2 log-domain (testing hook)
 extern std::atomic<int> g_last_qpadmm_kernel;    // 1 check-centric, 2 block-per-lane (testing hook)
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);

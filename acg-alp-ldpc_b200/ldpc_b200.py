@@ -77,6 +77,7 @@ def lib():
     L.ldpc_debug_bpmath.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
     L.ldpc_debug_bp_layout.argtypes = [vp, i32, vp]
     L.ldpc_debug_last_qpadmm_kernel.argtypes = []
+    L.ldpc_debug_last_bp_kernel.argtypes = []
     _lib = L
     return L
 
@@ -110,6 +111,11 @@ def debug_bpmath(a, ev, od, device=0):
     _check(lib().ldpc_debug_bpmath(device, a.size, a.ctypes.data, ev.ctypes.data, od.ctypes.data, out_exp.ctypes.data,
                                    out_log.ctypes.data))
     return out_exp, out_log
+
+
+def last_bp_kernel():
+    """1: the likelihood-ratio kernel served the last BP launch, 2: the log-domain kernel, 0: none yet"""
+    return int(lib().ldpc_debug_last_bp_kernel())
 
 
 def last_qpadmm_kernel():

@@ -235,6 +235,13 @@ def run_gpu(args):
 
         for i in range(warmup):
             step_device(i)
+        # which kernel served the launches (testing hooks of the C ABI): the headline must not come from a fall-back
+        if algo == "bp":
+            kernel = {1: "bp_lr_kernel", 2: "bp_kernel (log domain)"}[L.last_bp_kernel()]
+            assert L.last_bp_kernel() == 1, "the log-domain BP kernel served the benchmark code"
+        else:
+            kernel = {1: "qpadmm_chk_kernel", 2: "qpadmm_kernel (block per lane)"}[L.last_qpadmm_kernel()]
+            assert L.last_qpadmm_kernel() == 1, "the block-per-lane QP-ADMM kernel served the benchmark code"
         barrier()
         sampler = ClockSampler(local) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,6 +324,7 @@ def run_gpu(args):
             "e2e": {"value": world * e2e_frames * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": e2e_frames * n * 8, "d2h_bytes_per_step": e2e_frames * (n + 5)},
             "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),
+            "kernel": kernel,
         }
         if algo == "qpadmm":
             # shared-memory traffic of the check-centric kernel per frame-iteration: the row terms w are written once
@@ -356,13 +364,13 @@ def run_gpu(args):
                        "l2_policy": "inputs larger than L2: two alternating %d MB batches" % (
                            args.frames * 280 * 8 >> 20)},
             "info_gbit_per_s": bp["info_gbit_per_s"], "roofline": bp["roofline"], "e2e": bp["e2e"],
-            "clocks": bp["clocks"], "gpu_launches": args.steps, "cpu_baseline": cpu,
+            "clocks": bp["clocks"], "gpu_launches": args.steps, "kernel": bp["kernel"], "cpu_baseline": cpu,
             "qpadmm": {"metric": "decoded frames/sec (QP-ADMM, fixed 1000 iters, eps_stop=0)",
                        "config": {"workload": "QP-ADMM(alpha=%g, mu=%g, 1000 iters) on optimalH 160x280 @ %g dB" % (
                            ADMM_ALPHA, ADMM_MU, ADMM_SNR), "frames_per_step_per_gpu": admm["frames_per_step"]},
                        "value": admm["value"], "ms_per_step": admm["ms_per_step"],
                        "info_gbit_per_s": admm["info_gbit_per_s"], "roofline": admm["roofline"], "e2e": admm["e2e"],
-                       "clocks": admm["clocks"]},
+                       "clocks": admm["clocks"], "kernel": admm["kernel"]},
         }
         print(json.dumps(line))
     if world > 1:

@@ -207,6 +207,8 @@ int ldpc_debug_bp_layout(const ldpc_code_t *code, int32_t frames_per_cta, int32_
  * 1 = check-centric (qpadmm_chk_kernel.cu), 2 = block-per-lane (qpadmm_kernel.cu), 0 = none yet.  The parity tests
  * assert it, so a silent fall-back to the slower kernel fails them. */
 int ldpc_debug_last_qpadmm_kernel(void);
+/* ... and the last BP launch: 1 = likelihood-ratio kernel (bp_lr_kernel.cu), 2 = log-domain kernel (bp_kernel.cu). */
+int ldpc_debug_last_bp_kernel(void);
 
 #ifdef __cplusplus
 }

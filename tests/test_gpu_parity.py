@@ -92,6 +92,8 @@ def test_bp_matches_fp80_oracle(codes, oracle, name, snrs, frames):
     for snr in snrs:
         y = code.channel(SEED, 2000, frames, snr)
         gb, gok, git, gpost = code.bp_decode(y, snr, 100)
+        # every code of BASELINE.json is served by the likelihood-ratio kernel: a silent fall-back is a failure
+        assert _lib(codes).last_bp_kernel() == 1, "the log-domain kernel served %s" % name
         ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, snr, 100)
         bad = np.flatnonzero((gb != ob).any(1) | (gok != ook) | (git != oit))
         for f in bad:
@@ -120,6 +122,7 @@ def test_bp_multi_slot_kernels(codes, oracle, slots, monkeypatch):
         m, n = H.shape
         y = code.channel(SEED, 4000, frames, snr)
         gb, gok, git, gpost = code.bp_decode(y, snr, 100)
+        assert _lib(codes).last_bp_kernel() == (2 if slots == "log" else 1)
         ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, snr, 100)
         bad = np.flatnonzero((gb != ob).any(1) | (gok != ook) | (git != oit))
         for f in bad:
