@@ -61,6 +61,9 @@ struct AdmmChkParams {
     uint32_t off_w23, off_v, off_qa, off_inv, off_red, off_str, off_cw, off_ctl;
     int max_iter;
     double alpha, mu, eps_stop;
+    // derived penalty constants, computed on the host with the device's operations (IEEE double, no contraction): as
+    // kernel parameters they are constant-bank operands of the FP64 instructions instead of ten live registers
+    double half_mu, half_alpha, inv_aux, aux_init;
     int chunk;                    // frames claimed from the global queue at a time
     // grid mode (qpadmm_params.cpp:51-67): work item q of the queue = frame q % grid_frames under the parameters of
     // point q / grid_frames; counters per point
@@ -99,26 +102,38 @@ struct ChkShared {
 
 // One check with NBK blocks (degree NBK + 2), one frame.  va = the values of its variables in ascending index
 // order.  Writes the row terms of its blocks, updates yl / aux, returns the partial stop sum.
-template <int NBK, int NB>
+// MIXED: the warp holds checks of NBK and of NBK - 1 blocks (the boundary between two degree classes).  Instead of
+// running both code paths one after the other, the shorter checks (shrt) ride along: their last block takes the last
+// step (its variables, chunk and duals were placed there when the lane was set up), the step before it -- the longer
+// checks' last middle block -- is computed and discarded, and the auxiliary variable that joins their last two blocks
+// is moved into the place the last step reads and back.  Every lane performs exactly the operations of its own
+// check in the same order.
+template <int NBK, int NB, bool MIXED>
 __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double (&yl)[NB][4], double (&aux)[NB],
                                              uint32_t a_w01, uint32_t off_w23, const uint32_t (&plane_off)[NB],
-                                             double mu, double half_mu, double half_alpha, double inv_aux) {
+                                             double mu, double half_mu, double half_alpha, double inv_aux, bool shrt) {
     constexpr int D = NBK + 2;
     double part = 0.0, P = 0.0;
 #pragma unroll
     for (int k = 0; k < NBK; ++k) {
+        const bool skip = MIXED && shrt && k == NBK - 2;
+        if (MIXED && NBK >= 3 && k == NBK - 1) aux[k - 1] = shrt ? aux[k - 2] : aux[k - 1];
         double r0, r1, r2, r3;
         // the block's variables in ascending index order (originals before auxiliaries) and their slots
         if (NBK == 1) residual_rows<0, 1, 2>(va[0], va[1], va[2], 2.0, r0, r1, r2, r3);
         else if (k == 0) residual_rows<0, 1, 2>(va[0], va[1], aux[0], 2.0, r0, r1, r2, r3);
         else if (k == NBK - 1) residual_rows<1, 2, 0>(va[D - 2], va[D - 1], aux[k - 1], 2.0, r0, r1, r2, r3);
         else residual_rows<1, 0, 2>(va[k + 1], aux[k - 1], aux[k], 2.0, r0, r1, r2, r3);
+        const double part_in = part;
         const double w0 = row_update_fp<false>(r0, yl[k][0], part, mu, half_mu);
         const double w1 = row_update_fp<false>(r1, yl[k][1], part, mu, half_mu);
         const double w2 = row_update_fp<false>(r2, yl[k][2], part, mu, half_mu);
         const double w3 = row_update_fp<true>(r3, yl[k][3], part, mu, half_mu);
-        sts_f64x2(a_w01 + plane_off[k], w0, w1);
-        sts_f64x2(a_w01 + off_w23 + plane_off[k], w2, w3);
+        if (MIXED) part = skip ? part_in : part;
+        if (!skip) {
+            sts_f64x2(a_w01 + plane_off[k], w0, w1);
+            sts_f64x2(a_w01 + off_w23 + plane_off[k], w2, w3);
+        }
         // the auxiliary variable between blocks k-1 and k, for the next iteration (qp_admm.h:132-142 with q = 0):
         // rows of block k-1 (slot 2: -,-,+,+) then rows of block k (slot 0: +,-,-,+)
         if (k > 0) {
@@ -126,13 +141,16 @@ __device__ __forceinline__ double chk_update(const double (&va)[NB + 2], double 
             B = __dadd_rn(B, -w1);
             B = __dadd_rn(B, -w2);
             B = __dadd_rn(B, w3);
-            aux[k - 1] = clip01_int(__dmul_rn(B, inv_aux));
+            const double anew = clip01_int(__dmul_rn(B, inv_aux));
+            aux[k - 1] = skip ? aux[k - 1] : anew;
+            if (MIXED && NBK >= 3 && k == NBK - 1) aux[k - 2] = shrt ? aux[k - 1] : aux[k - 2];
         }
         if (k < NBK - 1) {
-            P = __dadd_rn(half_alpha, -w0);
-            P = __dadd_rn(P, -w1);
-            P = __dadd_rn(P, w2);
-            P = __dadd_rn(P, w3);
+            double Pn = __dadd_rn(half_alpha, -w0);
+            Pn = __dadd_rn(Pn, -w1);
+            Pn = __dadd_rn(Pn, w2);
+            Pn = __dadd_rn(Pn, w3);
+            P = skip ? P : Pn;
         }
     }
     return part;
@@ -210,9 +228,9 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
         S->alive = F;
     }
     // penalty parameters of this lane's frame slot (grid mode: reloaded whenever a new work item enters the slot)
-    double mu = p.mu, half_mu = __dmul_rn(p.mu, 0.5), half_alpha = __dmul_rn(p.alpha, 0.5);
-    double inv_aux = inv_coef(p.mu, p.alpha, 8.0);     // auxiliary variables: e = 8 (two blocks x four rows)
-    double aux_init = aux_start(mu, half_alpha, inv_aux);
+    double mu = p.mu, half_mu = p.half_mu, half_alpha = p.half_alpha;
+    double inv_aux = p.inv_aux;                        // auxiliary variables: e = 8 (two blocks x four rows)
+    double aux_init = p.aux_init;
 
     // ---- this lane's check (static): degree, variable offsets, chunk offsets
     const bool has_chk = cr < p.n_chk;
@@ -220,15 +238,33 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     uint32_t voff[NB + 2], plane_off[NB];
 #pragma unroll
     for (int j = 0; j < NB + 2; ++j) voff[j] = 0;
-    if (has_chk) {
-        const uint32_t *tab = p.chk_tab + (size_t) cr * p.tab_stride;
-        nb = (int) tab[0] - 2;
-#pragma unroll
-        for (int j = 0; j < NB + 2; ++j)
-            if (j < nb + 2) voff[j] = tab[1 + j] * (F * 8);
+    if (has_chk) nb = (int) p.chk_tab[(size_t) cr * p.tab_stride] - 2;
+    // a warp at the boundary of two degree classes whose block counts differ by one runs ONE code path (chk_update,
+    // MIXED): the shorter checks keep their last two variables and the chunk of their last block where the longer
+    // checks' last step looks for them
+    int mx = 0;                                    // 0: uniform warp, 1 / 2: a longer / shorter check of a mixed warp
+    {
+        const int nb_hi = __reduce_max_sync(0xffffffffu, has_chk ? nb : -100), nb_lo = __reduce_min_sync(0xffffffffu, has_chk ? nb : 100);
+        if (nb_hi == nb_lo + 1 && nb_lo >= 2) mx = nb == nb_lo ? 2 : 1;
     }
+    const bool shrt = mx == 2;
 #pragma unroll
     for (int k = 0; k < NB; ++k) plane_off[k] = (p.plane_base[k] + cr) * (F * 16);
+    if (has_chk) {
+        const uint32_t *tab = p.chk_tab + (size_t) cr * p.tab_stride;
+        // entry j of va: variable j of the check; for the shorter checks of a mixed warp the last two variables move
+        // up by one (entries nb + 1, nb + 2) and entry nb is a hole
+#pragma unroll
+        for (int j = 0; j < NB + 2; ++j) {
+            const int src = !shrt || j < nb ? j : (j == nb ? -1 : j - 1);
+            if (src >= 0 && src < nb + 2) voff[j] = tab[1 + src] * (F * 8);
+        }
+        if (shrt) {                                 // the chunk of their last block, where the last step stores
+#pragma unroll
+            for (int k = 2; k < NB; ++k)
+                if (k == nb) plane_off[k] = (p.plane_base[k - 1] + cr) * (F * 16);
+        }
+    }
     double yl[NB][4], aux[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -440,19 +476,28 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
         if (has_chk && ((run >> f) & 1u)) {
             double va[NB + 2];
 #pragma unroll
-            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2) ? lds_f64(a_vcur + voff[j]) : 0.0;
-#define LDPC_CHK_CASE(K)                                                                                          \
+            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2 + (mx >> 1)) ? lds_f64(a_vcur + voff[j]) : 0.0;
+#define LDPC_CHK_CASE(K, MIX)                                                                                     \
     case K:                                                                                                       \
         if (NB >= K)                                                                                              \
-            part = chk_update<(NB >= K ? K : 1), NB>(va, yl, aux, a_w01, p.off_w23, plane_off, mu, half_mu,       \
-                                                     half_alpha, inv_aux);                                        \
+            part = chk_update<(NB >= K ? K : 1), NB, MIX>(va, yl, aux, a_w01, p.off_w23, plane_off, mu, half_mu,  \
+                                                          half_alpha, inv_aux, mx == 2);                          \
         break;
-            switch (nb) {
-                case -1: part = chk_special<1>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
-                case 0: part = chk_special<2>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
-                LDPC_CHK_CASE(1) LDPC_CHK_CASE(2) LDPC_CHK_CASE(3) LDPC_CHK_CASE(4) LDPC_CHK_CASE(5) LDPC_CHK_CASE(6)
-                LDPC_CHK_CASE(7) LDPC_CHK_CASE(8) LDPC_CHK_CASE(9) LDPC_CHK_CASE(10)
-                default: break;
+            if (mx) {
+                switch (nb + (mx >> 1)) {
+                    LDPC_CHK_CASE(3, true) LDPC_CHK_CASE(4, true) LDPC_CHK_CASE(5, true) LDPC_CHK_CASE(6, true)
+                    LDPC_CHK_CASE(7, true) LDPC_CHK_CASE(8, true) LDPC_CHK_CASE(9, true) LDPC_CHK_CASE(10, true)
+                    default: break;
+                }
+            } else {
+                switch (nb) {
+                    case -1: part = chk_special<1>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
+                    case 0: part = chk_special<2>(va[0], va[1], yl[0][0], yl[0][1], a_w01, p.off_w23, plane_off[0], mu, half_mu); break;
+                    LDPC_CHK_CASE(1, false) LDPC_CHK_CASE(2, false) LDPC_CHK_CASE(3, false) LDPC_CHK_CASE(4, false)
+                    LDPC_CHK_CASE(5, false) LDPC_CHK_CASE(6, false) LDPC_CHK_CASE(7, false) LDPC_CHK_CASE(8, false)
+                    LDPC_CHK_CASE(9, false) LDPC_CHK_CASE(10, false)
+                    default: break;
+                }
             }
 #undef LDPC_CHK_CASE
         }
@@ -833,6 +878,23 @@ int qpadmm_chk_e_min(const ldpc_code *c) {
     return t->e_min;
 }
 
+// host twins of inv_coef / aux_start / clip01_int (the same IEEE operations in the same order; volatile keeps the
+// host compiler from contracting or reassociating them)
+static double host_inv_coef(double mu, double alpha, double e) {
+    volatile double t = mu * e;
+    volatile double A = (t - alpha) * 0.5;
+    volatile double d = 2.0 * A;
+    return -1.0 / d;
+}
+static double host_aux_start(double mu, double half_alpha, double inv_aux) {
+    volatile double w3 = mu * -2.0;                  // fma(mu, 0 - 2, 0): exact
+    volatile double B = half_alpha + w3;             // the additions of +-0 in between leave the sum unchanged
+    B = B + w3;
+    volatile double v = B * inv_aux;
+    if (!(v > 0.0)) return 0.0;
+    return v >= 1.0 ? 1.0 : (double) v;
+}
+
 int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, double alpha, double mu,
                       int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream,
                       const double *grid_alpha, const double *grid_mu, int64_t grid_points) {
@@ -840,14 +902,13 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     const bool grid = grid_points > 0;
     const int64_t frames_per_point = frames;
     if (grid) frames *= grid_points;             // work items of the queue
-    // frames per CTA: one lane per (check, frame), at most 640 lanes.  Two CTAs of two frames per SM beat one CTA
-    // of four (profiles/r01_admm_chk_sweep.txt): their barriers and their FP64-bound / latency-bound phases overlap.
-    int F = 2;
+    // frames per CTA: one lane per (check, frame), at most 640 lanes.  Four CTAs of one frame per SM beat two of two and
+    // one of four (profiles/r01_admm_chk_sweep.txt: 127.8 / 135.4 / 151 ms on optimalH, 124.6 / 129.2 / 150 ms on H05):
+    // their barriers and their FP64-bound / latency-bound phases overlap.
+    int F = 1;
     if (const char *force = getenv("LDPC_ADMM_F")) {
         const int v = atoi(force);
         if (v == 1 || v == 2 || v == 4) F = v;
-    } else {
-        while (F > 1 && frames < 2ll * 148 * F) F >>= 1;
     }
     const bool exp_mode = fio.experiment != 0;
     const AdmmChkTables *t = nullptr;
@@ -873,6 +934,9 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     p.special_lo = t->special_lo; p.special_hi = t->special_hi;
     p.n_chk = t->n_chk; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.tab_stride = t->tab_stride;
     p.max_iter = max_iter; p.alpha = alpha; p.mu = mu; p.eps_stop = eps_stop;
+    p.half_mu = mu * 0.5; p.half_alpha = alpha * 0.5;
+    p.inv_aux = host_inv_coef(mu, alpha, 8.0);
+    p.aux_init = host_aux_start(mu, p.half_alpha, p.inv_aux);
     p.grid_alpha = grid_alpha; p.grid_mu = grid_mu; p.grid_frames = frames_per_point;
     const int threads = chk_threads(c, F);
     const size_t smem = chk_smem_layout(c, *t, F, exp_mode, &p);
