@@ -554,19 +554,23 @@ static void chk_anneal(const ldpc_code *c, int F, int cols, const uint32_t *plan
     for (int i = 0; i < n; ++i) pos_of_var[var[i]] = i;
     auto col_of_pos = [&](int i) { const int j = i / cols, k = i % cols; return (j & 1) ? cols - 1 - k : k; };
     auto slot_of_pos = [&](int i) { return (i / cols) * cols + col_of_pos(i); };
+    // An 8-byte access is served half-warp by half-warp (16 lanes x 8 B = one 128-byte wavefront), a 16-byte access
+    // quarter-warp by quarter-warp (8 lanes x 16 B): a group is conflict-free iff its addresses fall into different
+    // positions of the 128-byte line, and costs (largest multiplicity - 1) replays otherwise.
+    const int ha = 16 / F, qc = 8 / F;               // checks per half-warp, columns per quarter-warp
     auto cost_a = [&](int g) {
         int cost = 0;
         const int r1 = std::min(m, g * G + G);
-        for (int j = 0; j < maxdeg; ++j) {
-            int cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, act = 0, worst = 0;
-            for (int i = g * G; i < r1; ++i) {
-                const int r = chk[i];
-                if (j >= cdeg(r)) continue;
-                ++act;
-                worst = std::max(worst, ++cnt[slot_of_pos(pos_of_var[c->col_idx[c->row_ptr[r] + j]]) % bins_a]);
+        for (int j = 0; j < maxdeg; ++j)
+            for (int h0 = g * G; h0 < r1; h0 += ha) {
+                int cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, worst = 1;
+                for (int i = h0; i < std::min(r1, h0 + ha); ++i) {
+                    const int r = chk[i];
+                    if (j >= cdeg(r)) continue;
+                    worst = std::max(worst, ++cnt[slot_of_pos(pos_of_var[c->col_idx[c->row_ptr[r] + j]]) % bins_a]);
+                }
+                cost += worst - 1;
             }
-            if (act) cost += worst - (act + bins_a - 1) / bins_a;
-        }
         return cost;
     };
     std::vector<int> chunks;                         // scratch: [column in warp][row] -> chunk, -1 beyond the end
@@ -589,16 +593,15 @@ static void chk_anneal(const ldpc_code *c, int F, int cols, const uint32_t *plan
             rows = std::max(rows, k);
         }
         int cost = 0;
-        for (int k = 0; k < rows; ++k) {
-            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, act = 0, worst = 0;
-            for (int x = 0; x < width; ++x) {
-                const int q = chunks[(size_t) x * cap + k];
-                if (q < 0) continue;
-                ++act;
-                worst = std::max(worst, ++cnt[q % bins_c]);
+        for (int k = 0; k < rows; ++k)
+            for (int x0 = 0; x0 < width; x0 += qc) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 1;
+                for (int x = x0; x < std::min(width, x0 + qc); ++x) {
+                    const int q = chunks[(size_t) x * cap + k];
+                    if (q >= 0) worst = std::max(worst, ++cnt[q % bins_c]);
+                }
+                cost += worst - 1;
             }
-            if (act) cost += worst - (act + bins_c - 1) / bins_c;
-        }
         return 2 * cost;                             // two 16-byte loads (w01, w23) per stream word
     };
     // class ranges (equal degree) by position
@@ -609,7 +612,9 @@ static void chk_anneal(const ldpc_code *c, int F, int cols, const uint32_t *plan
         if (i == n || vdeg(var[i]) != vdeg(var[s0])) { for (int k = s0; k < i; ++k) { v_lo[k] = s0; v_hi[k] = i; } s0 = i; }
     uint64_t rs = 0x9E3779B97F4A7C15ull;             // xorshift: the layout must not depend on the C++ library
     auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t) (rs >> 11); };
-    const int moves = 40 * (n + m);
+    int moves_per_node = 40;
+    if (const char *e = getenv("LDPC_ADMM_ANNEAL_MOVES")) moves_per_node = std::max(1, atoi(e));
+    const int moves = moves_per_node * (n + m);
     std::vector<int> ga, gc;
     auto uniq = [](std::vector<int> &x) { std::sort(x.begin(), x.end()); x.erase(std::unique(x.begin(), x.end()), x.end()); };
     auto replays = [&]() {
