@@ -608,6 +608,102 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                 }
             }
         }
+        // Fewer than 8 frames per CTA: a 16-byte access is served quarter-warp by quarter-warp (8 lanes = 16/F nodes of one
+        // step), and a node's frames fill only F/16 of a 128-byte line, so the 16/F nodes of a quarter-warp must sit in
+        // different positions of the line (slot mod 16/F) at every access or the wavefront is replayed (34 % of all
+        // shared-memory wavefronts of the (3,6)-1008 code at F = 2, profiles/r01_bp_lr_1008_ncu.txt).  The check pass is
+        // conflict-free by the odd class strides; for the variable pass a deterministic annealing pass permutes the
+        // variables inside their degree classes, the edges inside a variable's record and the edge positions inside a
+        // check -- all of it reorders independent work only.  Cost = replays (largest multiplicity - 1 per access).
+        if (F <= 4 && !getenv("LDPC_BP_NO_ANNEAL")) {
+            const int Q = 16 / F;                           // nodes per quarter-warp = positions per line
+            std::vector<int> cls_of(c->n, -1), pos_of(c->n, 0), chk_of_edge(c->E, 0);
+            for (size_t k = 0; k < c->var_classes.size(); ++k)
+                for (int i = 0; i < c->var_classes[k].count; ++i) {
+                    cls_of[var_ord[c->var_classes[k].first + i]] = (int) k;
+                    pos_of[var_ord[c->var_classes[k].first + i]] = i;
+                }
+            for (int r = 0; r < c->m; ++r)
+                for (int e = c->row_ptr[r]; e < c->row_ptr[r + 1]; ++e) chk_of_edge[e] = r;
+            auto group_cost = [&](int k, int g) {
+                const BpClass &cl = c->var_classes[k];
+                int cost = 0;
+                for (int j = 0; j < cl.degree; ++j) {
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 1;
+                    for (int i = g * Q; i < std::min(cl.count, g * Q + Q); ++i)
+                        worst = std::max(worst, ++cnt[slot_of_edge[var_edges[var_ord[cl.first + i]][j]] % Q]);
+                    cost += worst - 1;
+                }
+                return cost;
+            };
+            long now = 0;
+            for (size_t k = 0; k < c->var_classes.size(); ++k)
+                for (int g = 0; g * Q < c->var_classes[k].count; ++g) now += group_cost((int) k, g);
+            const long before = now;
+            long best = now;
+            std::vector<int> best_ord(var_ord), best_slot(slot_of_edge);
+            std::vector<std::vector<int>> best_edges(var_edges);
+            uint64_t rs = 0x9E3779B97F4A7C15ull;            // xorshift: the layout must not depend on the C++ library
+            auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t) (rs >> 11); };
+            const int moves = now > 0 ? 300 * c->n : 0;
+            for (int it = 0; it < moves && best > 0; ++it) {
+                const double temp = 0.5 * std::pow(0.02, (double) it / moves);
+                const uint32_t kind = rnd() % 3u;
+                int v1 = -1, v2 = -1, a = 0, b = 0, e1 = 0, e2 = 0;          // the (at most two) variables whose groups change
+                if (kind == 0) {                            // two variables of one class trade places
+                    v1 = (int) (rnd() % (uint32_t) c->n);
+                    if (cls_of[v1] < 0) continue;
+                    const BpClass &cl = c->var_classes[cls_of[v1]];
+                    v2 = var_ord[cl.first + (int) (rnd() % (uint32_t) cl.count)];
+                    if (v1 == v2) continue;
+                } else if (kind == 1) {                     // two edges of one variable trade places in its record
+                    v1 = (int) (rnd() % (uint32_t) c->n);
+                    const int d = (int) var_edges[v1].size();
+                    if (cls_of[v1] < 0 || d < 2) continue;
+                    a = (int) (rnd() % (uint32_t) d); b = (int) (rnd() % (uint32_t) d);
+                    if (a == b) continue;
+                } else {                                    // two edges of one check trade slots
+                    const int r = (int) (rnd() % (uint32_t) c->m), d = c->row_ptr[r + 1] - c->row_ptr[r];
+                    if (d < 2) continue;
+                    e1 = c->row_ptr[r] + (int) (rnd() % (uint32_t) d); e2 = c->row_ptr[r] + (int) (rnd() % (uint32_t) d);
+                    if (e1 == e2) continue;
+                    v1 = c->col_idx[e1]; v2 = c->col_idx[e2];
+                }
+                auto apply = [&]() {
+                    if (kind == 0) {
+                        const int k = cls_of[v1], p1 = pos_of[v1], p2 = pos_of[v2], f0 = c->var_classes[k].first;
+                        std::swap(var_ord[f0 + p1], var_ord[f0 + p2]);
+                        pos_of[v1] = p2; pos_of[v2] = p1;
+                    } else if (kind == 1) {
+                        std::swap(var_edges[v1][a], var_edges[v1][b]);
+                    } else {
+                        std::swap(slot_of_edge[e1], slot_of_edge[e2]);
+                    }
+                };
+                // groups touched: those of v1 and v2 before and after (a trade of places keeps the set)
+                int gk[2], gg[2], ng = 0;
+                for (int v : {v1, v2}) {
+                    if (v < 0) continue;
+                    const int k = cls_of[v], g = pos_of[v] / Q;
+                    if (ng == 1 && gk[0] == k && gg[0] == g) continue;
+                    gk[ng] = k; gg[ng] = g; ++ng;
+                }
+                int c0 = 0, c1 = 0;
+                for (int i = 0; i < ng; ++i) c0 += group_cost(gk[i], gg[i]);
+                apply();
+                for (int i = 0; i < ng; ++i) c1 += group_cost(gk[i], gg[i]);
+                const int delta = c1 - c0;
+                if (delta > 0 && (rnd() & 0xffffff) / 16777216.0 >= std::exp(-delta / temp)) {
+                    apply();                                // rejected: undo
+                } else {
+                    now += delta;
+                    if (now < best) { best = now; best_ord = var_ord; best_slot = slot_of_edge; best_edges = var_edges; }
+                }
+            }
+            var_ord = best_ord; slot_of_edge = best_slot; var_edges = best_edges;
+            if (getenv("LDPC_BP_LAYOUT_STATS"))
+                fprintf(stderr, "bp layout F=%d: variable-pass replays per iteration %ld -> %ld (%d moves)\n", F, before, best, moves);
+        }
         // L_ch / decision / posterior storage in variable-rank order (neighbouring lane groups -> neighbouring rows);
         // variables without edges follow
         std::vector<uint16_t> var_store(c->n, 0);
@@ -749,20 +845,24 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     const int rec_words = rec_words_of(c);
     // Frames per CTA.  Two CTAs of 8 frames per SM beat one CTA of 16 (47.0 vs 50.5 ms, profiles/r01_bp_lr_sweep.txt): the
     // FP64-bound check pass of one overlaps the shared-memory-bound variable pass of the other, and the parity layout
-    // of get_lr_schedule keeps the 64-byte rows of F = 8 conflict-free.
+    // of get_lr_schedule keeps the 64-byte rows of F = 8 conflict-free.  Larger codes: the largest F of which TWO CTAs
+    // fit an SM -- two CTAs of 2 frames beat one of 4 on the (3,6)-1008 code, 46.0 vs 48.8 ms (53.8 ms with 704 threads).
+    auto smem_of = [&](int f) { return lr_smem_bytes(c, c->E + c->m, f, p.soft, exp_mode, rec_words, 64 * 24); };
     int F = 8;
     if (const char *force = getenv("LDPC_BP_F")) {
         const int v = atoi(force);
         if (v == 2 || v == 4 || v == 8 || v == 16) F = v;
     } else {
         while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
+        while (F > 2 && 2 * smem_of(F) > 227 * 1024) F >>= 1;
     }
-    while (F > 2 && lr_smem_bytes(c, c->E + c->m, F, p.soft, exp_mode, rec_words, 64 * 24) > 227 * 1024) F >>= 1;
-    // warps per CTA: about three steps per warp and pass; at most 256 threads when two CTAs fit an SM, so that both
-    // run the 128-register variant
+    while (F > 2 && smem_of(F) > 227 * 1024) F >>= 1;
+    // warps per CTA: about three steps per warp and pass; at most 256 threads when two CTAs fit an SM, 512 when one does,
+    // so that the kernel runs the 128-register variant (one CTA of 4 frames on the (3,6)-1008 code: 48.8 ms with 512
+    // threads, 50.9 / 53.8 ms with 640 / 704 at 102 / 85 registers)
     const int lanes = std::max(c->n, c->m) * (F / 2);
-    const bool two_ctas = 2 * lr_smem_bytes(c, c->E + c->m, F, p.soft, exp_mode, rec_words, 64 * 24) <= 227 * 1024;
-    int threads = std::min(two_ctas ? 256 : 768, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
+    const bool two_ctas = 2 * smem_of(F) <= 227 * 1024;
+    int threads = std::min(two_ctas ? 256 : 512, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
         if (v >= 32 && v <= 768) threads = v;
