@@ -645,29 +645,53 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
             std::vector<std::vector<int>> best_edges(var_edges);
             uint64_t rs = 0x9E3779B97F4A7C15ull;            // xorshift: the layout must not depend on the C++ library
             auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t) (rs >> 11); };
-            const int moves = now > 0 ? 300 * c->n : 0;
+            int moves_per_node = 300;
+            if (const char *e = getenv("LDPC_BP_ANNEAL_MOVES")) moves_per_node = std::max(1, atoi(e));
+            const int moves = now > 0 ? moves_per_node * c->n : 0;
+            // checks of one class (equal degree): first slot of each, to let two checks trade their slot ranges
+            std::vector<int> chk_cls(c->m, -1), chk_base(c->m, 0);
+            for (size_t k = 0; k < c->chk_classes.size(); ++k)
+                for (int i = 0; i < c->chk_classes[k].count; ++i) {
+                    const int r = chk_ord[c->chk_classes[k].first + i];
+                    chk_cls[r] = (int) k;
+                    int lo = 1 << 30;
+                    for (int e = c->row_ptr[r]; e < c->row_ptr[r + 1]; ++e) lo = std::min(lo, slot_of_edge[e]);
+                    chk_base[r] = lo;
+                }
+            std::vector<int> touched, gk, gg;
             for (int it = 0; it < moves && best > 0; ++it) {
                 const double temp = 0.5 * std::pow(0.02, (double) it / moves);
-                const uint32_t kind = rnd() % 3u;
-                int v1 = -1, v2 = -1, a = 0, b = 0, e1 = 0, e2 = 0;          // the (at most two) variables whose groups change
+                const uint32_t kind = rnd() % 4u;
+                int v1 = -1, v2 = -1, a = 0, b = 0, e1 = 0, e2 = 0, r1 = -1, r2 = -1;
+                touched.clear();
                 if (kind == 0) {                            // two variables of one class trade places
                     v1 = (int) (rnd() % (uint32_t) c->n);
                     if (cls_of[v1] < 0) continue;
                     const BpClass &cl = c->var_classes[cls_of[v1]];
                     v2 = var_ord[cl.first + (int) (rnd() % (uint32_t) cl.count)];
                     if (v1 == v2) continue;
+                    touched = {v1, v2};
                 } else if (kind == 1) {                     // two edges of one variable trade places in its record
                     v1 = (int) (rnd() % (uint32_t) c->n);
                     const int d = (int) var_edges[v1].size();
                     if (cls_of[v1] < 0 || d < 2) continue;
                     a = (int) (rnd() % (uint32_t) d); b = (int) (rnd() % (uint32_t) d);
                     if (a == b) continue;
-                } else {                                    // two edges of one check trade slots
+                    touched = {v1};
+                } else if (kind == 2) {                     // two edges of one check trade slots
                     const int r = (int) (rnd() % (uint32_t) c->m), d = c->row_ptr[r + 1] - c->row_ptr[r];
                     if (d < 2) continue;
                     e1 = c->row_ptr[r] + (int) (rnd() % (uint32_t) d); e2 = c->row_ptr[r] + (int) (rnd() % (uint32_t) d);
                     if (e1 == e2) continue;
-                    v1 = c->col_idx[e1]; v2 = c->col_idx[e2];
+                    touched = {c->col_idx[e1], c->col_idx[e2]};
+                } else {                                    // two checks of one class trade their slot ranges
+                    r1 = (int) (rnd() % (uint32_t) c->m);
+                    if (chk_cls[r1] < 0) continue;
+                    const BpClass &cl = c->chk_classes[chk_cls[r1]];
+                    r2 = chk_ord[cl.first + (int) (rnd() % (uint32_t) cl.count)];
+                    if (r1 == r2 || ((chk_base[r1] ^ chk_base[r2]) & 1)) continue;      // keep the parity of the first slot
+                    for (int r : {r1, r2})
+                        for (int e = c->row_ptr[r]; e < c->row_ptr[r + 1]; ++e) touched.push_back(c->col_idx[e]);
                 }
                 auto apply = [&]() {
                     if (kind == 0) {
@@ -676,22 +700,27 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                         pos_of[v1] = p2; pos_of[v2] = p1;
                     } else if (kind == 1) {
                         std::swap(var_edges[v1][a], var_edges[v1][b]);
-                    } else {
+                    } else if (kind == 2) {
                         std::swap(slot_of_edge[e1], slot_of_edge[e2]);
+                    } else {
+                        const int shift = chk_base[r2] - chk_base[r1];
+                        for (int e = c->row_ptr[r1]; e < c->row_ptr[r1 + 1]; ++e) slot_of_edge[e] += shift;
+                        for (int e = c->row_ptr[r2]; e < c->row_ptr[r2 + 1]; ++e) slot_of_edge[e] -= shift;
+                        std::swap(chk_base[r1], chk_base[r2]);
                     }
                 };
-                // groups touched: those of v1 and v2 before and after (a trade of places keeps the set)
-                int gk[2], gg[2], ng = 0;
-                for (int v : {v1, v2}) {
-                    if (v < 0) continue;
+                // groups touched (a trade of places keeps the set of groups)
+                gk.clear(); gg.clear();
+                for (int v : touched) {
                     const int k = cls_of[v], g = pos_of[v] / Q;
-                    if (ng == 1 && gk[0] == k && gg[0] == g) continue;
-                    gk[ng] = k; gg[ng] = g; ++ng;
+                    bool seen = false;
+                    for (size_t i = 0; i < gk.size(); ++i) seen |= gk[i] == k && gg[i] == g;
+                    if (!seen) { gk.push_back(k); gg.push_back(g); }
                 }
                 int c0 = 0, c1 = 0;
-                for (int i = 0; i < ng; ++i) c0 += group_cost(gk[i], gg[i]);
+                for (size_t i = 0; i < gk.size(); ++i) c0 += group_cost(gk[i], gg[i]);
                 apply();
-                for (int i = 0; i < ng; ++i) c1 += group_cost(gk[i], gg[i]);
+                for (size_t i = 0; i < gk.size(); ++i) c1 += group_cost(gk[i], gg[i]);
                 const int delta = c1 - c0;
                 if (delta > 0 && (rnd() & 0xffffff) / 16777216.0 >= std::exp(-delta / temp)) {
                     apply();                                // rejected: undo
