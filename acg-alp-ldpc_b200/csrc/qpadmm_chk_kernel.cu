@@ -96,7 +96,7 @@ struct ChkShared {
     SlotBlock<F> S;
     ChkCtl c;
     double alpha[F], mu[F];       // grid mode: parameters of the slot's work item
-    double inv_tab[64][F];        // grid mode: inv_coef by e (sum of squared coefficients of the column, <= 60)
+    double inv_tab[64][F];        // inv_coef by e (sum of squared coefficients of the column, <= 60) under the slot's parameters
     int point[F];
 };
 
@@ -192,8 +192,10 @@ __device__ __forceinline__ double chk_special(double v0, double v1, double &yl0,
     return part;
 }
 
-template <int F, int NB, bool GRID>
-__global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(const AdmmChkParams p) {
+// TWO: 64 registers per thread, so that two CTAs of up to 512 lanes share an SM (large codes: one frame per CTA fills
+// 342..512 lanes, and at 96 registers a single CTA per SM has nobody to overlap its phases with)
+template <int F, int NB, bool GRID, bool TWO>
+__global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1) qpadmm_chk_kernel(const AdmmChkParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
     const int n = io.n;
@@ -213,9 +215,13 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     double *red_gen = reinterpret_cast<double *>(sm + p.off_red);
 
     slots_init(S);
-    for (int r = tid; r < p.n_slots; r += nt) {
-        reinterpret_cast<double *>(sm + p.off_inv)[r] = inv_coef(p.mu, p.alpha, (double) p.slot_e[r]);
-    }
+    // inv_coef by e (sum of squared coefficients of the variable's column, <= 60): one table per frame slot (grid mode
+    // refills a slot's column when a work item with other parameters enters it)
+    for (int i = tid; i < 64 * F; i += nt) L->inv_tab[i / F][i % F] = inv_coef(p.mu, p.alpha, (double) (i / F));
+    // ... and, where shared memory is not the limit, per slot: one load from a running address instead of a look-up
+    if (!TWO && !GRID)
+        for (int r = tid; r < p.n_slots; r += nt)
+            reinterpret_cast<double *>(sm + p.off_inv)[r] = inv_coef(p.mu, p.alpha, (double) p.slot_e[r]);
     for (int a = tid; a < p.stream_rows * (nt / F); a += nt)
         reinterpret_cast<uint32_t *>(sm + p.off_str)[a] = p.var_stream[a];
     if (tid < F) {                                        // the all-zero chunk
@@ -276,7 +282,6 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     const uint32_t a_v0 = sbase + p.off_v + f * 8;                  // + slot * F * 8   (second buffer: + vbuf)
     const uint32_t vbuf = (uint32_t) p.n_slots * F * 8;
     const uint32_t a_qa = sbase + p.off_qa + f * 8;
-    const uint32_t a_inv = sbase + p.off_inv;
     const uint32_t a_invtab = smem_addr(&L->inv_tab[0][0]) + f * 8;
     const uint32_t a_str = sbase + p.off_str + cr * 4;
     __syncthreads();
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
     B = __dadd_rn(B, flip_by(A23.x, W << 2));                                                                      \
     B = __dadd_rn(B, A23.y);                                                                                       \
     if (W & STR_LAST) {                                                                                            \
-        const double ic = GRID ? lds_f64(a_invtab + ((W >> 20) & 63u) * (F * 8)) : lds_f64(AI);                    \
+        const double ic = (GRID || TWO) ? lds_f64(a_invtab + ((W >> 20) & 63u) * (F * 8)) : lds_f64(AI);           \
         AQ += s_slot;                                                                                              \
         const double vnew = clip01_int(__dmul_rn(B, ic));                                                          \
         B = lds_f64(AQ);                                                                                           \
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(NB <= 6 ? 640 : 320, 1) qpadmm_chk_kernel(cons
         AV += s_slot;                                                                                              \
         AI += s_inv;                                                                                               \
     }
-            uint32_t a_s = a_str, a_q = a_qa + cr * (F * 8), a_vv = a_vcur + cr * (F * 8), a_i = a_inv + cr * 8;
+            uint32_t a_s = a_str, a_q = a_qa + cr * (F * 8), a_vv = a_vcur + cr * (F * 8), a_i = sbase + p.off_inv + cr * 8;
             uint32_t w = lds_u32(a_s);
             double2 a01 = lds_f64x2(a_w01 + (w & STR_OFF_MASK)), a23 = lds_f64x2(a_w23 + (w & STR_OFF_MASK));
             double B = lds_f64(a_q);
@@ -840,13 +845,13 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
 static size_t up16(size_t x) { return (x + 15) & ~(size_t) 15; }
 
 // carve-up of the dynamic shared memory; returns the total
-static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment, AdmmChkParams *p) {
+static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F, bool experiment, bool two, AdmmChkParams *p) {
     size_t off = 0;
     off += (size_t) (t.n_chunks + 1) * F * 16;           // w01 (+ the all-zero chunk)
     const size_t off_w23 = off; off += (size_t) (t.n_chunks + 1) * F * 16;
     const size_t off_v = off; off += (size_t) 2 * t.n_slots * F * 8;
     const size_t off_qa = off; off += (size_t) t.n_slots * F * 8;
-    const size_t off_inv = off; off += (size_t) t.n_slots * 8;
+    const size_t off_inv = off; off += two ? 0 : (size_t) t.n_slots * 8;     // two CTAs per SM: inv_coef is looked up by e instead
     const size_t off_red = off; off += (size_t) F * 32 * 8;
     const size_t off_str = off; off += (size_t) t.stream_rows * (chk_threads(c, F) / F) * 4;
     const size_t off_cw = off; off += experiment ? (size_t) F * c->n : 0;
@@ -862,18 +867,22 @@ static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F,
 using ChkKernel = void (*)(const AdmmChkParams);
 
 template <int F, bool GRID>
-static ChkKernel chk_kernel_for(int nb) {
-    if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID>;
-    if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID>;
-    if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID>;
-    if (nb == 6) return qpadmm_chk_kernel<F, 6, GRID>;
-    if (nb <= 8) return qpadmm_chk_kernel<F, 8, GRID>;
-    return qpadmm_chk_kernel<F, 10, GRID>;
+static ChkKernel chk_kernel_for(int nb, bool two) {
+    if (two && F == 1) {
+        if (nb <= 2) return qpadmm_chk_kernel<1, 2, GRID, true>;
+        if (nb <= 4) return qpadmm_chk_kernel<1, 4, GRID, true>;
+    }
+    if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID, false>;
+    if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID, false>;
+    if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID, false>;
+    if (nb == 6) return qpadmm_chk_kernel<F, 6, GRID, false>;
+    if (nb <= 8) return qpadmm_chk_kernel<F, 8, GRID, false>;
+    return qpadmm_chk_kernel<F, 10, GRID, false>;
 }
 
-static ChkKernel chk_kernel_for(int F, int nb, bool grid) {
-    if (grid) return F == 4 ? chk_kernel_for<4, true>(nb) : (F == 2 ? chk_kernel_for<2, true>(nb) : chk_kernel_for<1, true>(nb));
-    return F == 4 ? chk_kernel_for<4, false>(nb) : (F == 2 ? chk_kernel_for<2, false>(nb) : chk_kernel_for<1, false>(nb));
+static ChkKernel chk_kernel_for(int F, int nb, bool grid, bool two) {
+    if (grid) return F == 4 ? chk_kernel_for<4, true>(nb, two) : (F == 2 ? chk_kernel_for<2, true>(nb, two) : chk_kernel_for<1, true>(nb, two));
+    return F == 4 ? chk_kernel_for<4, false>(nb, two) : (F == 2 ? chk_kernel_for<2, false>(nb, two) : chk_kernel_for<1, false>(nb, two));
 }
 
 // smallest 4 x column degree: DecodeQPADMM answers {zeros, false} when e_min * mu <= alpha (qp_admm.h:108-114)
@@ -921,7 +930,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
         int st = get_chk_tables(c, F, &t);
         if (st) return st;
         if (!t->supported) return LDPC_E_UNSUPPORTED;
-        if (chk_threads(c, F) <= (t->max_nb <= 6 ? 640 : 320) && chk_smem_layout(c, *t, F, exp_mode, nullptr) <= 227 * 1024) break;
+        if (chk_threads(c, F) <= (t->max_nb <= 6 ? 640 : 320) && chk_smem_layout(c, *t, F, exp_mode, false, nullptr) <= 227 * 1024) break;
         if (F == 1) return LDPC_E_UNSUPPORTED;
     }
     if (!grid && (double) t->e_min * mu <= alpha) return LDPC_E_UNSUPPORTED;   // infeasible: the general kernel answers {zeros, false}
@@ -934,7 +943,6 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);     // grid mode: frames = work items
     io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
     p.chk_tab = t->chk_tab; p.var_slot = t->var_rank;
-    p.slot_e = t->var_e;
     for (int k = 0; k < CHK_MAX_NB; ++k) p.plane_base[k] = t->plane_base[k];
     p.special_lo = t->special_lo; p.special_hi = t->special_hi;
     p.n_chk = t->n_chk; p.n_slots = t->n_slots; p.n_chunks = t->n_chunks; p.tab_stride = t->tab_stride;
@@ -944,10 +952,16 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     p.aux_init = host_aux_start(mu, p.half_alpha, p.inv_aux);
     p.grid_alpha = grid_alpha; p.grid_mu = grid_mu; p.grid_frames = frames_per_point;
     const int threads = chk_threads(c, F);
-    const size_t smem = chk_smem_layout(c, *t, F, exp_mode, &p);
+    // one frame per CTA on 342..512 lanes: two CTAs per SM at 64 registers (a few spills) instead of one at 96 -- they
+    // overlap their phases: 277.7 -> 254.7 ms per 16384 x 1000 frame-iterations on the (3,6)-1008 code
+    bool two = F == 1 && threads > 341 && threads <= 512 && t->max_nb <= 4 &&
+               2 * chk_smem_layout(c, *t, F, exp_mode, true, nullptr) <= 227 * 1024;
+    if (const char *force = getenv("LDPC_ADMM_TWO")) two = two && atoi(force) != 0;
+    const size_t smem = chk_smem_layout(c, *t, F, exp_mode, two, &p);
     p.var_stream = t->var_stream;
     p.stream_rows = t->stream_rows;
-    ChkKernel fn = chk_kernel_for(F, t->max_nb, grid);
+    p.slot_e = t->var_e;
+    ChkKernel fn = chk_kernel_for(F, t->max_nb, grid, two);
     LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
