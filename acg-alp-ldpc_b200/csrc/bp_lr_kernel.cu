@@ -615,7 +615,7 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
         // conflict-free by the odd class strides; for the variable pass a deterministic annealing pass permutes the
         // variables inside their degree classes, the edges inside a variable's record and the edge positions inside a
         // check -- all of it reorders independent work only.  Cost = replays (largest multiplicity - 1 per access).
-        if (F <= 4 && !getenv("LDPC_BP_NO_ANNEAL")) {
+        if ((F <= 4 || (F == 8 && getenv("LDPC_BP_ANNEAL_F8"))) && !getenv("LDPC_BP_NO_ANNEAL")) {
             const int Q = 16 / F;                           // nodes per quarter-warp = positions per line
             std::vector<int> cls_of(c->n, -1), pos_of(c->n, 0), chk_of_edge(c->E, 0);
             for (size_t k = 0; k < c->var_classes.size(); ++k)
