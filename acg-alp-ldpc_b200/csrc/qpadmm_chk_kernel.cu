@@ -198,12 +198,10 @@ template <int F, int NB, bool GRID, bool TWO>
 __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1) qpadmm_chk_kernel(const AdmmChkParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
-    const int n = io.n;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int warp = tid >> 5, nwarps = nt >> 5, lane = tid & 31;
     const int f = tid % F, cr = tid / F;              // this lane's frame slot and check rank / variable column (static)
     const int cpt = nt / F;                           // variable slots between the steps of a lane
-    constexpr int LPF = 32 / F;                       // lanes of one frame in a warp
 
     char *sm = reinterpret_cast<char *>(smem);
     const uint32_t sbase = smem_addr(smem);

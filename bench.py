@@ -151,7 +151,7 @@ def run_reference(args):
     cores = host_cores()
     kind = "reference" if have_ref() else "port"
     if not have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so was not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so was not built"})
         return
     per_proc = max(2, int(round(args.ref_seconds / 0.07)))          # ~0.07 s per BP(100) frame per core
     for _ in range(args.warmup):
@@ -165,7 +165,7 @@ def run_reference(args):
     value = float(np.mean(vals))
     sample = "%d frames/step = %d procs x %d frames, BP(100) H05 @ %g dB, 1 thread per process" % (
         per_proc * cores, cores, per_proc, BP_SNR)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "decoded frames/sec (BP, fixed 100 iters)", "value": value,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -174,7 +174,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ----------------------------------------------------------------------- GPU arm
@@ -187,7 +187,6 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ.setdefault("NCCL_DEBUG", "WARN")       # no "NCCL version ..." banner on stdout: ONE JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -384,12 +383,35 @@ def run_gpu(args):
                        "info_gbit_per_s": admm["info_gbit_per_s"], "roofline": admm["roofline"], "e2e": admm["e2e"],
                        "clocks": admm["clocks"], "kernel": admm["kernel"]},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def guard_stdout():
+    """Everything any library prints to file descriptor 1 during the run (NCCL's version banner, a stray warning of
+    a child process) goes to stderr; only emit() reaches the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
