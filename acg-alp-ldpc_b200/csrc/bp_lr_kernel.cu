@@ -608,14 +608,15 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                 }
             }
         }
-        // Fewer than 8 frames per CTA: a 16-byte access is served quarter-warp by quarter-warp (8 lanes = 16/F nodes of one
+        // Fewer than 16 frames per CTA: a 16-byte access is served quarter-warp by quarter-warp (8 lanes = 16/F nodes of one
         // step), and a node's frames fill only F/16 of a 128-byte line, so the 16/F nodes of a quarter-warp must sit in
         // different positions of the line (slot mod 16/F) at every access or the wavefront is replayed (34 % of all
         // shared-memory wavefronts of the (3,6)-1008 code at F = 2, profiles/r01_bp_lr_1008_ncu.txt).  The check pass is
-        // conflict-free by the odd class strides; for the variable pass a deterministic annealing pass permutes the
+        // conflict-free by the odd class strides; for the variable pass the parity construction above is the starting point
+        // (at F = 8 it leaves 38 of 430 accesses of H05 replayed, 4 after the polish) and a deterministic annealing pass permutes the
         // variables inside their degree classes, the edges inside a variable's record and the edge positions inside a
         // check -- all of it reorders independent work only.  Cost = replays (largest multiplicity - 1 per access).
-        if ((F <= 4 || (F == 8 && getenv("LDPC_BP_ANNEAL_F8"))) && !getenv("LDPC_BP_NO_ANNEAL")) {
+        if (F <= 8 && !getenv("LDPC_BP_NO_ANNEAL")) {
             const int Q = 16 / F;                           // nodes per quarter-warp = positions per line
             std::vector<int> cls_of(c->n, -1), pos_of(c->n, 0), chk_of_edge(c->E, 0);
             for (size_t k = 0; k < c->var_classes.size(); ++k)
