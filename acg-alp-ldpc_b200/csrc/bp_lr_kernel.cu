@@ -873,26 +873,27 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     }
     const bool exp_mode = fio.experiment != 0;
     const int rec_words = rec_words_of(c);
-    // Frames per CTA.  Two CTAs of 8 frames per SM beat one CTA of 16 (47.0 vs 50.5 ms, profiles/r01_bp_lr_sweep.txt): the
-    // FP64-bound check pass of one overlaps the shared-memory-bound variable pass of the other, and the parity layout
-    // of get_lr_schedule keeps the 64-byte rows of F = 8 conflict-free.  Larger codes: the largest F of which TWO CTAs
-    // fit an SM -- two CTAs of 2 frames beat one of 4 on the (3,6)-1008 code, 46.0 vs 48.8 ms (53.8 ms with 704 threads).
+    // Frames per CTA and CTAs per SM.  Several small CTAs per SM beat one large one: the FP64-bound check pass of one
+    // overlaps the shared-memory-bound variable pass of another, and a small CTA refills its frame slots sooner
+    // (profiles/r01_bp_lr_sweep.txt: H05, fixed iterations: one CTA of 16 frames 50.5 ms, two of 8 45.6 ms, four of 4
+    // 45.6 ms; as run at -3 dB 31.8 vs 31.0 ms for two / four; optimalH 47.6 vs 46.6 ms; (3,6)-1008: one CTA of 4 frames
+    // 48.8 ms, two of 2 46.0 ms before the layout annealing).  The kernel needs 128 registers per thread, i.e. 512 threads
+    // per SM: four CTAs of 4 frames x 128 threads where their messages fit, else two CTAs of the largest F that fits twice
+    // x 256 threads, else one CTA x 512 threads.
     auto smem_of = [&](int f) { return lr_smem_bytes(c, c->E + c->m, f, p.soft, exp_mode, rec_words, 64 * 24); };
     int F = 8;
     if (const char *force = getenv("LDPC_BP_F")) {
         const int v = atoi(force);
         if (v == 2 || v == 4 || v == 8 || v == 16) F = v;
     } else {
+        if (4 * smem_of(4) <= 227 * 1024) F = 4;
         while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
         while (F > 2 && 2 * smem_of(F) > 227 * 1024) F >>= 1;
     }
     while (F > 2 && smem_of(F) > 227 * 1024) F >>= 1;
-    // warps per CTA: about three steps per warp and pass; at most 256 threads when two CTAs fit an SM, 512 when one does,
-    // so that the kernel runs the 128-register variant (one CTA of 4 frames on the (3,6)-1008 code: 48.8 ms with 512
-    // threads, 50.9 / 53.8 ms with 640 / 704 at 102 / 85 registers)
     const int lanes = std::max(c->n, c->m) * (F / 2);
-    const bool two_ctas = 2 * smem_of(F) <= 227 * 1024;
-    int threads = std::min(two_ctas ? 256 : 512, std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
+    const int ctas_per_sm = (int) std::min<size_t>(4, std::max<size_t>(1, (227 * 1024) / smem_of(F)));
+    int threads = std::min(ctas_per_sm >= 4 ? 128 : (ctas_per_sm >= 2 ? 256 : 512), std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
     if (const char *force = getenv("LDPC_BP_THREADS")) {
         const int v = atoi(force) / 32 * 32;
         if (v >= 32 && v <= 768) threads = v;
