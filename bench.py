@@ -10,7 +10,8 @@ H05 code (160 x 280), AWGN frames at -5 dB.  One "step" = one batch of
 steps.  -5 dB is used because there the reference's BP (which cannot switch its
 syndrome exit off) also runs all 100 iterations on >= 99.8 % of frames, so the CPU
 arm does the same work on the same kind of input.  QP-ADMM (optimalH, 1000 fixed
-iterations, eps_stop = 0) is measured in the same run and reported under "qpadmm".
+iterations, eps_stop = 0) is measured in the same run and reported under "qpadmm"; both decoders on the
+synthetic (3,6)-regular n = 1008 code (configs[3]) under "reg_3_6_1008".
 
 One JSON line on stdout (rank 0).  Keys follow the driver's contract; the
 roofline is the FP64 pipe (messages never leave the SM, so HBM traffic is ~0.1 %
@@ -41,7 +42,8 @@ BP_SMEM_BYTES_PER_EDGE_ITER = 32.0    # each message is read and written once pe
 BP_SMEM_BYTES_PER_VAR_ITER = 8.0      # channel likelihood ratio
 # DRAM traffic per frame from the ncu --set full captures of the two kernels (dram__bytes_read.sum + dram__bytes_write.sum
 # over the frames of the captured launch, profiles/r01_bp_lr_final_ncu.txt / r01_admm_chk_final_ncu.txt): the y samples
-# (n x 8 B = 2240 B) and nothing else -- the outputs stay in L2 until after the kernel
+# (n x 8 B = 2240 B for n = 280) and nothing else -- the outputs stay in L2 until after the kernel; scaled by n / 280 for the
+# (3,6)-1008 code (its captures, profiles/r01_bp_lr_1008_ncu.txt / r01_admm_chk_1008_ncu.txt: 8.1 KB per frame)
 NCU_DRAM_BYTES_PER_FRAME = {"bp": 10.724e6 / 4736, "qpadmm": 5.396e6 / 2368}
 # QP-ADMM, check-centric kernel: per three-variable block and iteration
 ADMM_FP64_PER_BLOCK_ITER = 47.0       # 9 residual + 25 row updates (6 per row, 7 for row 3) + 6.5 auxiliary update + 6.5 variable update
@@ -322,12 +324,12 @@ def run_gpu(args):
             smem_bytes = info["edges"] * BP_SMEM_BYTES_PER_EDGE_ITER + info["n"] * BP_SMEM_BYTES_PER_VAR_ITER
             got = fps_gpu * n_iter * smem_bytes / 1e9
             roof = {"bound": "smem", "achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
-                    "traffic": NCU_DRAM_BYTES_PER_FRAME["bp"] * frames, "bytes_per_frame_iter": smem_bytes,
+                    "traffic": NCU_DRAM_BYTES_PER_FRAME["bp"] * frames * n / 280.0, "bytes_per_frame_iter": smem_bytes,
                     "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)",
                     "work_per_launch": "%d frames x %d iters x %.0f B of shared-memory traffic" % (frames, n_iter, smem_bytes),
                     "fp64": fp64, "hbm": hbm}
         else:
-            roof = dict(fp64, bound="fp64", traffic=NCU_DRAM_BYTES_PER_FRAME["qpadmm"] * frames, hbm=hbm)
+            roof = dict(fp64, bound="fp64", traffic=NCU_DRAM_BYTES_PER_FRAME["qpadmm"] * frames * n / 280.0, hbm=hbm)
         res = {
             "value": value, "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
             "info_gbit_per_s": value * k / 1e9,
@@ -352,6 +354,9 @@ def run_gpu(args):
 
     bp = bench_algo("bp", "H05", args.frames, args.steps, args.warmup)
     admm = bench_algo("qpadmm", "optimalH", max(1024, args.frames // 8), args.steps, args.warmup)
+    # the other code north_star names: synthetic (3,6)-regular n = 1008 (BASELINE.json configs[3]), same settings
+    big_bp = bench_algo("bp", "reg_3_6_1008", max(1024, args.frames // 4), args.steps, args.warmup)
+    big_admm = bench_algo("qpadmm", "reg_3_6_1008", max(512, args.frames // 16), args.steps, args.warmup)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -382,6 +387,14 @@ def run_gpu(args):
                        "value": admm["value"], "ms_per_step": admm["ms_per_step"],
                        "info_gbit_per_s": admm["info_gbit_per_s"], "roofline": admm["roofline"], "e2e": admm["e2e"],
                        "clocks": admm["clocks"], "kernel": admm["kernel"]},
+            "reg_3_6_1008": {
+                "config": {"workload": "synthetic (3,6)-regular 504x1008 (configs[3]): BP(100 fixed iters) @ %g dB, %d frames/step/GPU; "
+                                       "QP-ADMM(alpha=%g, mu=%g, 1000 fixed iters) @ %g dB, %d frames/step/GPU" % (
+                                           BP_SNR, big_bp["frames_per_step"], ADMM_ALPHA, ADMM_MU, ADMM_SNR,
+                                           big_admm["frames_per_step"])},
+                "bp": {k: big_bp[k] for k in ("value", "ms_per_step", "info_gbit_per_s", "roofline", "e2e", "clocks", "kernel")},
+                "qpadmm": {k: big_admm[k] for k in ("value", "ms_per_step", "info_gbit_per_s", "roofline", "e2e", "clocks", "kernel")},
+            },
         }
         emit(line)
     if world > 1:
