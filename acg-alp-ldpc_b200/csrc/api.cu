@@ -125,24 +125,33 @@ int decode_host(const ldpc_code *c, const DecodeCfg &cfg, const double *y, int64
         if ((st = slot_reserve(slots[s], (size_t) chunk, n, soft != nullptr))) return st;
     }
     // the first chunk is small: its copy-in is the only one no kernel hides
-    int which = 0;
-    int64_t cnt = 0;
-    for (int64_t begin = 0; begin < frames; begin += cnt, which ^= 1) {
-        Slot &s = slots[which];
-        cnt = std::min(begin == 0 && frames > chunk ? std::max<int64_t>(chunk / 8, 1) : chunk, frames - begin);
-        LDPC_CUDA(cudaMemcpyAsync(s.y, y + begin * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, s.stream));
-        FrameIO io;
-        io.y = s.y; io.bits = s.bits; io.ok = s.ok; io.iters = s.iters; io.soft = soft ? s.soft : nullptr;
-        if ((st = enqueue_decode(c, cfg, io, cnt, s.queue, s.stream))) return st;
-        LDPC_CUDA(cudaMemcpyAsync(bits + begin * n, s.bits, cnt * n, cudaMemcpyDeviceToHost, s.stream));
-        LDPC_CUDA(cudaMemcpyAsync(ok + begin, s.ok, cnt, cudaMemcpyDeviceToHost, s.stream));
-        LDPC_CUDA(cudaMemcpyAsync(iters + begin, s.iters, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (soft)
-            LDPC_CUDA(cudaMemcpyAsync(soft + begin * n, s.soft, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost,
-                                      s.stream));
-    }
-    LDPC_CUDA(cudaStreamSynchronize(slots[0].stream));
-    LDPC_CUDA(cudaStreamSynchronize(slots[1].stream));
+    // On a failure in the middle of the loop the work already queued still reads the caller's y and writes the caller's
+    // output buffers: both streams are drained before the status is returned (secondary errors are ignored).
+    auto pipeline = [&]() -> int {
+        int which = 0;
+        int64_t cnt = 0;
+        for (int64_t begin = 0; begin < frames; begin += cnt, which ^= 1) {
+            Slot &s = slots[which];
+            cnt = std::min(begin == 0 && frames > chunk ? std::max<int64_t>(chunk / 8, 1) : chunk, frames - begin);
+            LDPC_CUDA(cudaMemcpyAsync(s.y, y + begin * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, s.stream));
+            FrameIO io;
+            io.y = s.y; io.bits = s.bits; io.ok = s.ok; io.iters = s.iters; io.soft = soft ? s.soft : nullptr;
+            int st2;
+            if ((st2 = enqueue_decode(c, cfg, io, cnt, s.queue, s.stream))) return st2;
+            LDPC_CUDA(cudaMemcpyAsync(bits + begin * n, s.bits, cnt * n, cudaMemcpyDeviceToHost, s.stream));
+            LDPC_CUDA(cudaMemcpyAsync(ok + begin, s.ok, cnt, cudaMemcpyDeviceToHost, s.stream));
+            LDPC_CUDA(cudaMemcpyAsync(iters + begin, s.iters, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s.stream));
+            if (soft)
+                LDPC_CUDA(cudaMemcpyAsync(soft + begin * n, s.soft, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost,
+                                          s.stream));
+        }
+        return LDPC_OK;
+    };
+    st = pipeline();
+    const cudaError_t e0 = cudaStreamSynchronize(slots[0].stream), e1 = cudaStreamSynchronize(slots[1].stream);
+    if (st) return st;
+    if (e0 != cudaSuccess) return cuda_fail(e0, "decode stream 0", __FILE__, __LINE__);
+    if (e1 != cudaSuccess) return cuda_fail(e1, "decode stream 1", __FILE__, __LINE__);
     return LDPC_OK;
 }
 
@@ -295,6 +304,12 @@ int ldpc_qpadmm_grid_run(const ldpc_code_t *c, int32_t points, const double *alp
                          uint64_t *counters, double *gpu_seconds) {
     if (!c || !alpha || !mu || !counters || points < 0) return fail(LDPC_E_INVALID, "bad argument");
     if (max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
+    if (codeword_source < LDPC_CW_ZERO || codeword_source > LDPC_CW_GENERATOR)
+        return fail(LDPC_E_INVALID, "unknown codeword source");
+    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
+        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
+    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
+        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
     if (gpu_seconds) *gpu_seconds = 0.0;
     for (int64_t i = 0; i < (int64_t) points * LDPC_CNT_COUNT; ++i) counters[i] = 0;
     if (points == 0 || frame_count == 0) return LDPC_OK;
@@ -316,10 +331,6 @@ int ldpc_qpadmm_grid_run(const ldpc_code_t *c, int32_t points, const double *alp
         if (gpu_seconds) *gpu_seconds += secs;
     }
     if (batch.empty()) return LDPC_OK;
-    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
-        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
-    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
-        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
     LDPC_CUDA(cudaSetDevice(c->device));
     Slot &s = g_ctx.per_device[c->device][0];
     int st = slot_init(s);

@@ -160,7 +160,7 @@ extern std::atomic<int> g_last_bp_kernel;        // 1 likelihood-ratio, 2 log-do
 extern std::atomic<int> g_last_qpadmm_kernel;    // 1 check-centric, 2 block-per-lane (testing hook)
 int launch_qpadmm(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                   double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream);
-// the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 3..8) and block-per-lane (any code)
+// the two QP-ADMM kernels behind launch_qpadmm: check-centric (checks of degree 0..12, variables of at most 15 edges) and block-per-lane (any code)
 // grid_points > 0: `frames` frames under each of grid_points (alpha, mu) pairs (device arrays), counters per point
 int launch_qpadmm_chk(const ldpc_code *code, const FrameIO &io, int64_t frames, double var, double alpha,
                       double mu, int max_iter, double eps_stop, unsigned long long *queue, cudaStream_t stream,

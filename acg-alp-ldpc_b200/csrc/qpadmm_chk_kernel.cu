@@ -435,10 +435,11 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
             if (S->alive == 0) break;
             const unsigned fresh = L->c.fresh;
             if (fresh) {
-                if (GRID && tid < 64 * F) {          // inv_coef of the slot's parameters by e
-                    const int q = tid % F, e = tid / F;
-                    if ((fresh >> q) & 1u) L->inv_tab[e][q] = inv_coef(L->mu[q], L->alpha[q], (double) e);
-                }
+                if (GRID)                            // inv_coef of the slot's parameters by e (a CTA may have as few as 32 threads)
+                    for (int i = tid; i < 64 * F; i += nt) {
+                        const int q = i % F, e = i / F;
+                        if ((fresh >> q) & 1u) L->inv_tab[e][q] = inv_coef(L->mu[q], L->alpha[q], (double) e);
+                    }
                 // z = yl = 0 (qp_admm.h:120-121): w = mu (0 - b) -- the first variable phase of the frame reads it
                 for (int i = tid; i < p.n_chunks * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) {

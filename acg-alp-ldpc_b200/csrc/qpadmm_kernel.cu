@@ -291,10 +291,12 @@ static AdmmKernel kernel_for(int F, int kb) {
 
 // Frames per CTA (F) and blocks per lane (KB): the shape that keeps the most lanes busy per SM, i.e.
 // resident warps (registers and shared memory both limit them) x the fraction of lanes that own a block.
-static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int *per_sm_out) {
+static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int *per_sm_out, bool ignore_env = false) {
     int want_f = 0, want_kb = 0;
-    if (const char *s = getenv("LDPC_ADMM_F")) want_f = atoi(s);
-    if (const char *s = getenv("LDPC_ADMM_KB")) want_kb = atoi(s);
+    if (!ignore_env) {
+        if (const char *s = getenv("LDPC_ADMM_F")) want_f = atoi(s);
+        if (const char *s = getenv("LDPC_ADMM_KB")) want_kb = atoi(s);
+    }
     double best_score = -1;
     for (int F = 4; F >= 1; F >>= 1) {
         if ((want_f == 1 || want_f == 2 || want_f == 4) && F != want_f) continue;
@@ -318,17 +320,14 @@ static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int 
             if (score > best_score + 1e-9) { best_score = score; *out = s; *per_sm_out = per_sm; }
         }
     }
-    if (best_score < 0 && (want_f || want_kb)) {      // a forced shape that does not fit: fall back to the heuristic
-        unsetenv("LDPC_ADMM_F");
-        unsetenv("LDPC_ADMM_KB");
-        return choose_shape(c, frames, out, per_sm_out);
-    }
+    if (best_score < 0 && (want_f || want_kb))        // a forced shape that does not fit: fall back to the heuristic
+        return choose_shape(c, frames, out, per_sm_out, true);   // (the caller's environment is left alone)
     if (best_score < 0)
         return fail(LDPC_E_UNSUPPORTED, "QP-ADMM state of this code exceeds one SM (shared memory / threads)");
     return LDPC_OK;
 }
 
-// Decoder::decode / exp() for QP-ADMM: the check-centric kernel where it applies (all checks of degree 3..8, a
+// Decoder::decode / exp() for QP-ADMM: the check-centric kernel where it applies (all checks of degree 0..12, a
 // feasible (alpha, mu)), else the block-per-lane kernel below; LDPC_ADMM_KERNEL=block|check overrides (A/B runs).
 // which kernel served the last QP-ADMM launch of this process (ldpc_debug_last_qpadmm_kernel): 1 check-centric, 2 block-per-lane
 std::atomic<int> g_last_qpadmm_kernel{0};

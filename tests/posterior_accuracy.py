@@ -26,7 +26,9 @@ def mp_bp(H, y, snr, iters, mp):
     var = mp.mpf(10) ** (-mp.mpf(snr) / 10) / 2
     llr = [2 * mp.mpf(float(v)) / var for v in y]
     rows = [np.flatnonzero(H[r]) for r in range(m)]
-    phi = lambda x: -mp.log(mp.tanh(x / 2))
+    # phi(x) = -log(tanh(x/2)) = 2 atanh(exp(-x)): this form keeps full relative accuracy at every magnitude (the
+    # log/tanh form returns 0 once exp(-x) drops below the working precision)
+    phi = lambda x: 2 * mp.atanh(mp.exp(-x))
     v2c = {(r, v): llr[v] for r in range(m) for v in rows[r]}
     post = None
     for _ in range(iters):
