@@ -46,39 +46,45 @@
 #include <cstring>
 
 #include "bpmath.cuh"
-#include "slots_multi.cuh"
+#include "slots_team.cuh"
+#include "smem_ptx.cuh"
 
 namespace ldpc {
 
-constexpr int LR_MAX_DEGREE = 64;
+constexpr int LR_MAX_UNROLLED = 8;           // larger degrees take the generic routines (kernel variant WIDE)
+constexpr int LR_MAX_DEGREE = 16;            // bp_lr_cap() >= 50 implies degrees <= 14
 
 struct BpLrParams {
     KernelIO io;
     const uint32_t *rec_v;      // variable records (words): [var * F * 8, slot_0 * F * 8, ..., slot_{d-1} * F * 8], padded to 4 words
-    const uint32_t *steps;      // per warp: steps_per_warp words, variable pass then check pass, each list ends with 0
+    const uint32_t *steps;      // step words of one team: check pass (steps_c rows of `gt` words), then variable pass (steps_v rows)
     const uint16_t *var_store;  // variable index -> storage index of its L_ch / decision / posterior (rank order)
-    int pad_even;               // 1: the checks of an even-degree class are stored with stride degree + 1 (see host side)
     int rec_words;              // total words of rec_v
-    int steps_per_warp, steps_c_off;
-    int E;
+    int steps_c, steps_v;       // rows of the two step tables (the last row of each is all zero)
+    int gt;                     // threads per team
+    int E;                      // message slots per frame (including the idle ones of padded classes)
+    // byte offsets inside a team's region of shared memory, and the size of a region
+    uint32_t off_lch, off_post, off_dec, off_cw, off_ctl, team_bytes;
+    uint32_t off_teams;         // start of the teams' regions (behind the shared tables)
     int max_iter, early_exit;
     int clamp_lo, clamp_hi;     // high words of exp(-C1), exp(+C1)
     double llr_cap;
     int chunk;                  // frames claimed from the global queue at a time
-    int soft;                   // posterior array present
 };
 
-// A step = one warp instruction's worth of nodes of one degree: 64/F consecutive ranks, one per lane group.
-//   bits 0-17  byte offset (variable pass: of the first node record in the shared record table;
-//              check pass: of the first message of the first node)
-//   bits 18-22 nodes in the step - 1
-//   bits 23-29 degree (0 = end of list)
-__host__ __device__ __forceinline__ uint32_t lr_step_word(uint32_t first, int nodes, int degree) {
-    return first | ((uint32_t) (nodes - 1) << 18) | ((uint32_t) degree << 23);
+// A step = one warp instruction's worth of nodes of one degree: 64/F consecutive ranks, one per lane group.  Every
+// thread of a team has its own word per step (row k of the table at [k * gt + thread]):
+//   bits 0-17  byte offset of the lane's work: check pass -- the first message of its node; variable pass -- the node's
+//              record in the record table
+//   bit 23     the lane is idle in this step (the class does not fill the step)
+//   bits 24-31 degree (0 = end of the list); the lists are sorted by descending degree
+constexpr uint32_t LR_STEP_OFF = 0x3ffffu, LR_STEP_IDLE = 1u << 23;
+__host__ __device__ __forceinline__ uint32_t lr_step_word(uint32_t off, bool idle, int degree) {
+    return off | (idle ? LR_STEP_IDLE : 0u) | ((uint32_t) degree << 24);
 }
 
-// control words of a trip, double-buffered by trip parity (written by warp 0 during the
-// variable phase of trip k for trip k+1)
+// control words of a trip, double-buffered by trip parity (written by warp 0 of the team during the variable phase of
+// trip k for trip k+1)
 struct LrCtl {
     unsigned active;    // slots whose messages are valid V->C messages (they take part in the check pass)
     unsigned elig;      // slots with iter >= 1 (the reference tests the syndrome from iteration 1 on, bp.h:195)
@@ -98,15 +104,16 @@ struct LrShared {
 __device__ __forceinline__ double ld_f64(const char *p) { return *reinterpret_cast<const double *>(p); }
 __device__ __forceinline__ void st_f64(char *p, double v) { *reinterpret_cast<double *>(p) = v; }
 
-// two frames of one element
+// two frames of one element; the hot loops address shared memory through 32-bit shared-window addresses (smem_ptx.cuh):
+// one register per base address, register + immediate per access
 struct P2 {
     double a, b;
 };
-__device__ __forceinline__ P2 ld_p2(const char *p) {
-    const double2 t = *reinterpret_cast<const double2 *>(p);
+__device__ __forceinline__ P2 ld_p2(uint32_t a) {
+    const double2 t = lds_f64x2(a);
     return P2{t.x, t.y};
 }
-__device__ __forceinline__ void st_p2(char *p, P2 v) { *reinterpret_cast<double2 *>(p) = make_double2(v.a, v.b); }
+__device__ __forceinline__ void st_p2(uint32_t a, P2 v) { sts_f64x2(a, v.a, v.b); }
 __device__ __forceinline__ P2 operator*(P2 x, P2 y) { return P2{x.a * y.a, x.b * y.b}; }
 __device__ __forceinline__ P2 fma2(P2 x, P2 y, P2 z) { return P2{__fma_rn(x.a, y.a, z.a), __fma_rn(x.b, y.b, z.b)}; }
 __device__ __forceinline__ P2 div2(P2 x, P2 y) { return P2{div_pos(x.a, y.a), div_pos(x.b, y.b)}; }
@@ -118,27 +125,32 @@ __device__ __forceinline__ double clamp_sign(double x, int neg_lo, int range, in
     return __hiloint2double(__viaddmin_s32_relu(__double2hiint(x), neg_lo, range) + lo_sign, __double2loint(x));
 }
 
+// shared-window base addresses of a lane (team region + the lane's frame pair)
+struct LrAddr {
+    uint32_t msg, dec;          // messages (L_ch: + off_lch, posteriors: + off_post, both uniform), decisions
+    uint32_t off_lch, off_post;
+};
+
 // ---- variable node of degree D, two frames: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
-// rec = the node's record in shared memory; msg_p / lch_p / post_p / dec_p already point at the lane's frame pair.
+// rec = shared-window address of the node's record
 template <int D, bool SOFT>
-__device__ __forceinline__ void lr_var_update(char *msg_p, const char *lch_p, char *post_p, uint8_t *dec_p,
-                                              const uint32_t *rec, int d_runtime, int clamp_lo, int clamp_hi) {
+__device__ __forceinline__ void lr_var_update(const LrAddr &A, uint32_t rec, int d_runtime, int clamp_lo, int clamp_hi) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
     uint32_t w[CAP + 4];
     if (D > 0) {
 #pragma unroll
         for (int q = 0; q < (D + 1 + 3) / 4; ++q) {
-            const uint4 t = *(reinterpret_cast<const uint4 *>(rec) + q);
+            const uint4 t = lds_u32x4(rec + 16 * q);
             w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
         }
     } else {
-        for (int q = 0; q <= d; ++q) w[q] = rec[q];
+        for (int q = 0; q <= d; ++q) w[q] = lds_u32(rec + 4 * q);
     }
-    const P2 lc = ld_p2(lch_p + w[0]);
+    const P2 lc = ld_p2(A.msg + A.off_lch + w[0]);
     P2 x[CAP], suf[CAP], lam[CAP];
 #pragma unroll
-    for (int j = 0; j < d; ++j) x[j] = ld_p2(msg_p + w[1 + j]);
+    for (int j = 0; j < d; ++j) x[j] = ld_p2(A.msg + w[1 + j]);
     suf[d - 1] = P2{1.0, 1.0};
 #pragma unroll
     for (int j = d - 2; j >= 0; --j) suf[j] = (j == d - 2) ? x[j + 1] : suf[j + 1] * x[j + 1];
@@ -154,15 +166,16 @@ __device__ __forceinline__ void lr_var_update(char *msg_p, const char *lch_p, ch
     const int neg_lo = -clamp_lo, range = clamp_hi - clamp_lo;
 #pragma unroll
     for (int j = 0; j < d; ++j)
-        st_p2(msg_p + w[1 + j], P2{clamp_sign(lam[j].a, neg_lo, range, sa), clamp_sign(lam[j].b, neg_lo, range, sb)});
-    *reinterpret_cast<uint16_t *>(dec_p + (w[0] >> 3)) = (uint16_t) ((one_a ? 1 : 0) | (one_b ? 0x100 : 0));
-    if (SOFT) st_p2(post_p + w[0], tot);
+        st_p2(A.msg + w[1 + j], P2{clamp_sign(lam[j].a, neg_lo, range, sa), clamp_sign(lam[j].b, neg_lo, range, sb)});
+    sts_u16(A.dec + (w[0] >> 3), (uint32_t) ((one_a ? 1 : 0) | (one_b ? 0x100 : 0)));
+    if (SOFT) st_p2(A.msg + A.off_post + w[0], tot);
 }
 
 // ---- check node of degree D, two frames: CNode::message (bp.h:49-57); returns the parities of the decisions
-// (bit 0 / bit 1 = first / second frame of the pair).  edge = first message of the node, lane's frame pair.
+// (bit 0 / bit 1 = first / second frame of the pair).  edge = shared-window address of the first message of the node,
+// lane's frame pair.
 template <int D, int FB>
-__device__ __forceinline__ int lr_chk_update(char *edge, int d_runtime, int clamp_hi) {
+__device__ __forceinline__ int lr_chk_update(uint32_t edge, int d_runtime, int clamp_hi) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
     P2 a[CAP], se[CAP], so[CAP];
@@ -204,31 +217,44 @@ __device__ __forceinline__ int lr_chk_update(char *edge, int d_runtime, int clam
     return par;
 }
 
-template <int F, int MAXT>
+// Several TEAMS per CTA: a team is `gt` threads with F frames in flight, its own region of shared memory and its own
+// named barrier; the read-only tables (variable records, step lists) are held once per CTA.  One CTA per SM, as many
+// teams as shared memory and registers allow: the teams never wait for one another, so their FP64-bound check passes and
+// shared-memory-bound variable passes overlap.
+// SOFT: posterior likelihood ratios are kept (soft output requested).  WIDE: degrees above 8 occur (generic routines).
+template <int F, int MAXT, bool SOFT, bool WIDE>
 __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
-    const int n = io.n;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31;
     constexpr int FB = F * 8;                   // bytes between consecutive elements
     constexpr int LPN = F / 2;                  // lanes per node
-    const int pair = lane % LPN, node_lane = lane / LPN;
+    const int gt = p.gt;
+    const int team = threadIdx.x / gt;
+    Team T;
+    T.tid = threadIdx.x - team * gt;
+    T.nt = gt;
+    T.bar = 1 + team;
+    const int tid = T.tid, nt = gt;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pair = lane % LPN;
 
-    char *msg = reinterpret_cast<char *>(smem);                          // E x F doubles
-    char *lch = msg + (size_t) p.E * FB;                                 // n x F doubles
-    char *post = lch + (size_t) n * FB;                                  // n x F doubles (soft output only)
-    uint32_t *rec = reinterpret_cast<uint32_t *>(post + (p.soft ? (size_t) n * FB : 0));   // variable records
-    uint32_t *steps = rec + p.rec_words;                                 // this CTA's copy of the step lists
-    uint8_t *dec = reinterpret_cast<uint8_t *>(steps + (size_t) (nt >> 5) * p.steps_per_warp);   // n x F bytes
-    uint8_t *cw = dec + (size_t) n * F;                                  // F x n bytes (experiment mode)
-    LrShared<F> *L = reinterpret_cast<LrShared<F> *>(
-        (reinterpret_cast<uintptr_t>(cw + (io.experiment ? (size_t) n * F : 0)) + 15) & ~(uintptr_t) 15);
+    // shared tables
+    uint32_t *rec = reinterpret_cast<uint32_t *>(smem);                  // variable records
+    uint32_t *steps = rec + p.rec_words;                                 // step words: check pass, variable pass
+    for (int i = threadIdx.x; i < p.rec_words; i += blockDim.x) rec[i] = p.rec_v[i];
+    for (int i = threadIdx.x; i < (p.steps_c + p.steps_v) * gt; i += blockDim.x) steps[i] = p.steps[i];
+
+    // this team's region
+    char *base = reinterpret_cast<char *>(smem) + p.off_teams + (size_t) team * p.team_bytes;
+    char *msg = base;                                                    // E x F doubles
+    char *lch = base + p.off_lch;                                        // n x F doubles
+    char *post = base + p.off_post;                                      // n x F doubles (soft output only)
+    uint8_t *dec = reinterpret_cast<uint8_t *>(base + p.off_dec);        // n x F bytes
+    uint8_t *cw = reinterpret_cast<uint8_t *>(base + p.off_cw);          // F x n bytes (experiment mode)
+    LrShared<F> *L = reinterpret_cast<LrShared<F> *>(base + p.off_ctl);
     SlotBlock<F> *S = &L->S;
 
-    slots_init(S);
-    for (int i = tid; i < p.rec_words; i += nt) rec[i] = p.rec_v[i];
-    for (int i = tid; i < (nt >> 5) * p.steps_per_warp; i += nt) steps[i] = p.steps[i];
+    team_slots_init(T, S);
     if (tid == 0) {
         L->ctl[0] = LrCtl{0u, 0u, 0u, 0u};
         L->ctl[1] = LrCtl{0u, 0u, 0u, 0u};
@@ -237,16 +263,27 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         L->q_next = L->q_end = 0;
         S->alive = F;
     }
-    __syncthreads();
+    __syncthreads();                            // the only CTA-wide barrier: tables are in place
 
-    char *msg_p = msg + pair * 16;
-    const char *lch_p = lch + pair * 16;
-    char *post_p = post + pair * 16;
-    uint8_t *dec_p = dec + pair * 2;
-    const bool soft = p.soft != 0;
-    const uint32_t *my_steps_v = steps + (size_t) warp * p.steps_per_warp;
-    const uint32_t *my_steps_c = my_steps_v + p.steps_c_off;
-    const unsigned pair_bits = 3u << (2 * pair);
+    // shared-window addresses of this lane's share
+    // (They take a round trip through shared memory: a value ptxas can derive from the thread index is recomputed at
+    // every step instead of being kept -- fourteen instructions per step; a loaded value stays in its register.)
+    LrAddr A;
+    {
+        const uint32_t scratch = smem_addr(msg) + tid * 16;
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "r"(smem_addr(msg) + pair * 16),
+                     "r"(smem_addr(dec) + pair * 2), "r"(smem_addr(steps) + tid * 4), "r"(2u * pair) : "memory");
+    }
+    T.sync();
+    const uint4 kept = lds_u32x4(smem_addr(msg) + tid * 16);
+    T.sync();
+    A.msg = kept.x;
+    A.dec = kept.y;
+    A.off_lch = p.off_lch;
+    A.off_post = p.off_post;
+    const uint32_t a_steps_c = kept.z, a_steps_v = a_steps_c + p.steps_c * gt * 4;
+    const uint32_t a_rec = smem_addr(rec), row = (uint32_t) gt * 4;
+    const unsigned pair_shift = kept.w, pair_bits = 3u << pair_shift;
 
     for (unsigned trip = 0;; ++trip) {
         LrCtl *ctl = &L->ctl[trip & 1];
@@ -255,39 +292,43 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         if (active) {
             unsigned bad = 0;
             if (active & pair_bits) {
-                const uint32_t *q = my_steps_c;
-                uint32_t e = *q;
-#define LDPC_CHK_STEPS(D, COND)                                                                             \
-    while (COND) {                                                                                          \
-        const uint32_t nx = *++q;                                                                           \
-        const int deg = (int) (e >> 23);                                                                    \
-        if (node_lane <= (int) ((e >> 18) & 31u))                                                           \
-            bad |= (unsigned) lr_chk_update<D, FB>(msg_p + (e & 0x3ffffu) + node_lane * (deg | p.pad_even) * FB, deg, p.clamp_hi); \
+                // the step word of a busy lane is offset + (degree << 24): inside the loop of degree D the address is one add
+                uint32_t q = a_steps_c;
+                uint32_t e = lds_u32(q);
+                if (WIDE) {
+                    while (e >= ((uint32_t) (LR_MAX_UNROLLED + 1) << 24)) {
+                        const uint32_t nx = lds_u32(q += row);
+                        if (!(e & LR_STEP_IDLE)) bad |= (unsigned) lr_chk_update<0, FB>(A.msg + (e & LR_STEP_OFF), (int) (e >> 24), p.clamp_hi);
+                        e = nx;
+                    }
+                }
+#define LDPC_CHK_STEPS(D)                                                                                   \
+    while (e >= ((uint32_t) (D) << 24)) {                                                                   \
+        const uint32_t nx = lds_u32(q += row);                                                              \
+        if (!(e & LR_STEP_IDLE)) bad |= (unsigned) lr_chk_update<D, FB>(A.msg + e - ((uint32_t) (D) << 24), D, p.clamp_hi); \
         e = nx;                                                                                             \
     }
-                LDPC_CHK_STEPS(0, (e >> 23) > 8)
-                LDPC_CHK_STEPS(8, (e >> 23) == 8) LDPC_CHK_STEPS(7, (e >> 23) == 7) LDPC_CHK_STEPS(6, (e >> 23) == 6)
-                LDPC_CHK_STEPS(5, (e >> 23) == 5) LDPC_CHK_STEPS(4, (e >> 23) == 4) LDPC_CHK_STEPS(3, (e >> 23) == 3)
-                LDPC_CHK_STEPS(2, (e >> 23) == 2) LDPC_CHK_STEPS(1, (e >> 23) == 1)
+                LDPC_CHK_STEPS(8) LDPC_CHK_STEPS(7) LDPC_CHK_STEPS(6) LDPC_CHK_STEPS(5)
+                LDPC_CHK_STEPS(4) LDPC_CHK_STEPS(3) LDPC_CHK_STEPS(2) LDPC_CHK_STEPS(1)
 #undef LDPC_CHK_STEPS
             }
-            const unsigned b = __reduce_or_sync(0xffffffffu, bad << (2 * pair));
+            const unsigned b = __reduce_or_sync(0xffffffffu, bad << pair_shift);
             if (lane == 0 && b) atomicOr(&ctl->bad, b);
         }
-        __syncthreads();
+        T.sync();
 
         // ---- publish finished frames, refill their slots
         const unsigned okmask = ctl->elig & ~ctl->bad & active;          // syndrome vanished (iteration >= 1)
         const unsigned finmask = (ctl->atmax | (p.early_exit ? okmask : 0u)) & active;
         if (finmask || trip == 0) {
             if (finmask)
-                slots_finish_all<F>(io, S, finmask, okmask, cw,
-                                    [&](int i, int f) { return (int) dec[(size_t) p.var_store[i] * F + f]; },
-                                    [&](int i, int f) {
-                                        const double t = ld_f64(post + (size_t) p.var_store[i] * FB + f * 8);
-                                        return log_pos(fmin(fmax(t, 1e-300), 1e300));
-                                    });
-            __syncthreads();
+                team_slots_finish_all<F>(T, io, S, finmask, okmask, cw,
+                                         [&](int i, int f) { return (int) dec[(size_t) p.var_store[i] * F + f]; },
+                                         [&](int i, int f) {
+                                             const double t = ld_f64(post + (size_t) p.var_store[i] * FB + f * 8);
+                                             return log_pos(fmin(fmax(t, 1e-300), 1e300));
+                                         });
+            T.sync();
             if (warp == 0) {
                 // lanes f < F own slot f: empty slots take the next frame of the locally claimed range
                 const unsigned live_before = L->live & ~finmask;
@@ -322,7 +363,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
                     S->alive = F - __popc(dead);
                 }
             }
-            __syncthreads();
+            T.sync();
             if (S->alive == 0) break;
             const unsigned fresh = L->fresh;
             if (fresh) {
@@ -331,12 +372,12 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
                 for (int i = tid; i < p.E * F; i += nt)
                     if ((fresh >> (i % F)) & 1u) st_f64(msg + (size_t) i * 8, 1.0);
                 // L_ch = exp(llr), llr clamped to +-llr_cap; variables without edges keep decision / posterior of the channel
-                slots_load_all<F>(io, S, fresh, cw, [&](int i, int f, double l) {
+                team_slots_load_all<F>(T, io, S, fresh, cw, [&](int i, int f, double l) {
                     const double lc = exp_signed(fmin(fmax(l, -p.llr_cap), p.llr_cap));
                     const size_t st = p.var_store[i];
                     st_f64(lch + st * FB + f * 8, lc);
                     dec[st * F + f] = (uint8_t) (lc <= 1.0);
-                    if (p.soft) st_f64(post + st * FB + f * 8, lc);
+                    if (SOFT) st_f64(post + st * FB + f * 8, lc);
                 });
             }
         }
@@ -360,37 +401,51 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
             }
         }
         if (live & pair_bits) {
-            const uint32_t *q = my_steps_v;
-            uint32_t e = *q;
-#define LDPC_VAR_STEPS(D, COND)                                                                                   \
-    while (COND) {                                                                                                \
-        const uint32_t nx = *++q;                                                                                 \
-        const int deg = (int) (e >> 23);                                                                          \
-        if (node_lane <= (int) ((e >> 18) & 31u)) {                                                               \
-            const int words = ((deg + 1 + 3) / 4) * 4;                                                            \
-            const uint32_t *r = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(rec) + (e & 0x3ffffu)) + node_lane * words; \
-            if (soft) lr_var_update<D, true>(msg_p, lch_p, post_p, dec_p, r, deg, p.clamp_lo, p.clamp_hi);        \
-            else lr_var_update<D, false>(msg_p, lch_p, post_p, dec_p, r, deg, p.clamp_lo, p.clamp_hi);            \
-        }                                                                                                         \
+            uint32_t q = a_steps_v;
+            uint32_t e = lds_u32(q);
+            if (WIDE) {
+                while (e >= ((uint32_t) (LR_MAX_UNROLLED + 1) << 24)) {
+                    const uint32_t nx = lds_u32(q += row);
+                    if (!(e & LR_STEP_IDLE)) lr_var_update<0, SOFT>(A, a_rec + (e & LR_STEP_OFF), (int) (e >> 24), p.clamp_lo, p.clamp_hi);
+                    e = nx;
+                }
+            }
+#define LDPC_VAR_STEPS(D)                                                                                         \
+    while (e >= ((uint32_t) (D) << 24)) {                                                                         \
+        const uint32_t nx = lds_u32(q += row);                                                                    \
+        if (!(e & LR_STEP_IDLE)) lr_var_update<D, SOFT>(A, a_rec + e - ((uint32_t) (D) << 24), D, p.clamp_lo, p.clamp_hi); \
         e = nx;                                                                                                   \
     }
-            LDPC_VAR_STEPS(0, (e >> 23) > 8)
-            LDPC_VAR_STEPS(8, (e >> 23) == 8) LDPC_VAR_STEPS(7, (e >> 23) == 7) LDPC_VAR_STEPS(6, (e >> 23) == 6)
-            LDPC_VAR_STEPS(5, (e >> 23) == 5) LDPC_VAR_STEPS(4, (e >> 23) == 4) LDPC_VAR_STEPS(3, (e >> 23) == 3)
-            LDPC_VAR_STEPS(2, (e >> 23) == 2) LDPC_VAR_STEPS(1, (e >> 23) == 1)
+            LDPC_VAR_STEPS(8) LDPC_VAR_STEPS(7) LDPC_VAR_STEPS(6) LDPC_VAR_STEPS(5)
+            LDPC_VAR_STEPS(4) LDPC_VAR_STEPS(3) LDPC_VAR_STEPS(2) LDPC_VAR_STEPS(1)
 #undef LDPC_VAR_STEPS
         }
-        __syncthreads();
+        T.sync();
     }
-    slots_flush(io, S);
+    team_slots_flush(T, io, S);
 }
 
 // ---------------------------------------------------------------- host side
 
-static size_t lr_smem_bytes(const ldpc_code *c, int n_slots, int F, bool soft, bool experiment, int rec_words, int step_words) {
-    return (size_t) F * 8 * ((size_t) n_slots + (size_t) c->n * (soft ? 2 : 1)) + (size_t) F * c->n * (experiment ? 2 : 1) +
-           (size_t) 4 * (rec_words + step_words) + 16 + sizeof(SlotBlock<32>) + 256;
+static size_t up16(size_t x) { return (x + 15) & ~(size_t) 15; }
+
+// a team's region of shared memory: messages, L_ch, posteriors (soft output), decisions, codewords (experiment mode),
+// control block; fills the offsets of `p` when given
+static size_t lr_team_bytes(const ldpc_code *c, int n_slots, int F, bool soft, bool experiment, BpLrParams *p) {
+    size_t off = (size_t) n_slots * F * 8;
+    const size_t off_lch = off; off += (size_t) c->n * F * 8;
+    const size_t off_post = off; off += soft ? (size_t) c->n * F * 8 : 0;
+    const size_t off_dec = off; off += (size_t) c->n * F;
+    const size_t off_cw = off; off += experiment ? (size_t) c->n * F : 0;
+    const size_t off_ctl = up16(off); off = up16(off_ctl + sizeof(LrShared<16>));
+    if (p) {
+        p->off_lch = (uint32_t) off_lch; p->off_post = (uint32_t) off_post; p->off_dec = (uint32_t) off_dec;
+        p->off_cw = (uint32_t) off_cw; p->off_ctl = (uint32_t) off_ctl; p->team_bytes = (uint32_t) off;
+    }
+    return off;
 }
+
+constexpr size_t LR_SMEM_MAX = 227 * 1024;
 
 // message cap C1: products of (dv - 1) messages times L_ch, and of (dc - 1) messages, must stay inside the double range
 double bp_lr_cap(const ldpc_code *c, double *llr_cap_out) {
@@ -408,38 +463,50 @@ static int rec_words_of(const ldpc_code *c) {
     return words;
 }
 
-// Deals the steps (64/F consecutive node ranks of one degree class = one node per lane group) to the warps so that
-// the warps of a pass finish together: longest-processing-time first onto the least loaded warp, with the executed
-// instructions of a step as its cost (body + fixed part, profiles/r01_bp_lr_final_ncu.txt).  Per warp: its steps by
-// descending degree (the kernel runs one loop per degree), terminated by a 0 word.
-template <typename FirstOf>
-static std::vector<std::vector<uint32_t>> deal_steps(const std::vector<BpClass> &classes, int F, int nwarps, bool check_pass,
-                                                     FirstOf first_of) {
-    const int G = 64 / F;
-    struct Step { uint32_t word; int degree, cost; };
+// Deals the steps (64/F consecutive node ranks of one degree class = one node per lane group) to the warps of a team so
+// that the warps of a pass finish together: longest-processing-time first onto the least loaded warp, with the executed
+// instructions of a step as its cost.  Per warp: its steps by descending degree (the kernel runs one loop per degree).
+// The result is one word per (step row, thread of the team): row k at [k * gt + thread], the row after a warp's last
+// step is zero.  offset_of(class, node rank in class) = byte offset of the node's work (check pass: its first message;
+// variable pass: its record); the lane's frame pair is part of the lane's base address.
+template <typename OffsetOf>
+static std::vector<uint32_t> deal_steps(const std::vector<BpClass> &classes, int F, int nwarps, bool check_pass, OffsetOf offset_of,
+                                        int *rows_out) {
+    const int G = 64 / F, LPN = F / 2;
+    struct Step { int cls, node0, degree, cost; };
     std::vector<Step> all;
     for (size_t k = 0; k < classes.size(); ++k)
         for (int n0 = 0; n0 < classes[k].count; n0 += G) {
             const int d = classes[k].degree;
-            all.push_back(Step{lr_step_word(first_of((int) k, n0), std::min(G, classes[k].count - n0), d), d,
-                               check_pass ? 12 + 33 * d : 32 + 18 * d});
+            all.push_back(Step{(int) k, n0, d, check_pass ? 12 + 33 * d : 32 + 18 * d});
         }
     std::stable_sort(all.begin(), all.end(), [](const Step &a, const Step &b) { return a.cost > b.cost; });
     std::vector<std::vector<Step>> mine(nwarps);
     std::vector<long> load(nwarps, 0);
-    const bool round_robin = getenv("LDPC_BP_DEAL_RR") != nullptr;     // the previous dealing, for comparison runs
     for (size_t i = 0; i < all.size(); ++i) {
-        int w = (int) (i % nwarps);
-        if (!round_robin) w = (int) (std::min_element(load.begin(), load.end()) - load.begin());
+        const int w = (int) (std::min_element(load.begin(), load.end()) - load.begin());
         mine[w].push_back(all[i]);
         load[w] += all[i].cost;
     }
-    std::vector<std::vector<uint32_t>> per_warp(nwarps);
+    size_t rows = 1;
     for (int w = 0; w < nwarps; ++w) {
         std::stable_sort(mine[w].begin(), mine[w].end(), [](const Step &a, const Step &b) { return a.degree > b.degree; });
-        for (const Step &st : mine[w]) per_warp[w].push_back(st.word);
+        rows = std::max(rows, mine[w].size() + 1);
     }
-    return per_warp;
+    const int gt = nwarps * 32;
+    std::vector<uint32_t> words(rows * gt, 0u);
+    for (int w = 0; w < nwarps; ++w)
+        for (size_t k = 0; k < mine[w].size(); ++k) {
+            const Step &st = mine[w][k];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int node_lane = lane / LPN;
+                const bool idle = st.node0 + node_lane >= classes[st.cls].count;
+                const uint32_t off = idle ? 0u : offset_of(st.cls, st.node0 + node_lane);
+                words[k * gt + w * 32 + lane] = lr_step_word(off, idle, st.degree);
+            }
+        }
+    *rows_out = (int) rows;
+    return words;
 }
 
 template <typename T>
@@ -774,25 +841,21 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
                     F, clash_v, pairs_v, clash_c, pairs_c);
         if (rec.size() * 4 >= (1u << 18) || (size_t) n_slots * F * 8 >= (1u << 18))
             return fail(LDPC_E_UNSUPPORTED, "code too large for the 18-bit step offsets of the BP kernel");
-        auto sv = deal_steps(c->var_classes, F, nwarps, false, [&](int cls, int node0) {
-            return first_v[cls] + (uint32_t) node0 * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 16);
-        });
-        auto sc = deal_steps(c->chk_classes, F, nwarps, true, [&](int cls, int node0) {
-            return (uint32_t) (class_slot0[cls] + node0 * (c->chk_classes[cls].degree | pad_even)) * F * 8;
-        });
-        size_t mv = 1, mc = 1;
-        for (int w = 0; w < nwarps; ++w) { mv = std::max(mv, sv[w].size() + 1); mc = std::max(mc, sc[w].size() + 1); }
-        std::vector<uint32_t> steps((size_t) nwarps * (mv + mc), 0u);
-        for (int w = 0; w < nwarps; ++w) {
-            std::copy(sv[w].begin(), sv[w].end(), steps.begin() + (size_t) w * (mv + mc));
-            std::copy(sc[w].begin(), sc[w].end(), steps.begin() + (size_t) w * (mv + mc) + mv);
-        }
+        int rows_c = 0, rows_v = 0;
+        std::vector<uint32_t> sc = deal_steps(c->chk_classes, F, nwarps, true, [&](int cls, int node) {
+            return (uint32_t) (class_slot0[cls] + node * (c->chk_classes[cls].degree | pad_even)) * F * 8;
+        }, &rows_c);
+        std::vector<uint32_t> sv = deal_steps(c->var_classes, F, nwarps, false, [&](int cls, int node) {
+            return first_v[cls] + (uint32_t) node * (uint32_t) (((c->var_classes[cls].degree + 1 + 3) / 4) * 16);
+        }, &rows_v);
+        std::vector<uint32_t> steps(sc);
+        steps.insert(steps.end(), sv.begin(), sv.end());
         s.rec_words = (int) rec.size();
         s.n_slots = n_slots;
         s.pad_even = pad_even;
         s.clash_v = clash_v; s.pairs_v = pairs_v; s.clash_c = clash_c; s.pairs_c = pairs_c;
-        s.steps_per_warp = (int) (mv + mc);
-        s.steps_c_off = (int) mv;
+        s.steps_c = rows_c;
+        s.steps_v = rows_v;
         int st;
         if ((st = upload_vec(&s.var_store, var_store))) return st;
         if ((st = upload_vec(&s.rec_v, rec))) return st;
@@ -803,32 +866,30 @@ static int get_lr_schedule(const ldpc_code *c, int F, int nwarps, BpLrSchedule *
     return LDPC_OK;
 }
 
+using LrKernel = void (*)(const BpLrParams);
+
 template <int F, int MAXT>
-static int launch_lr_ft(BpLrParams &p, const ldpc_code *c, int threads, int64_t frames, cudaStream_t stream) {
-    BpLrSchedule s;
-    int st = get_lr_schedule(c, F, threads / 32, &s);
-    if (st) return st;
-    p.rec_v = s.rec_v; p.steps = s.steps; p.rec_words = s.rec_words;
-    p.steps_per_warp = s.steps_per_warp; p.steps_c_off = s.steps_c_off;
-    p.var_store = s.var_store; p.pad_even = s.pad_even; p.E = s.n_slots;      // message slots including the idle ones
-    const size_t smem = lr_smem_bytes(c, s.n_slots, F, p.soft != 0, p.io.experiment != 0, s.rec_words, s.steps_per_warp * (threads / 32));
-    if (smem > 227 * 1024) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
-    auto kernel = bp_lr_kernel<F, MAXT>;
-    LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    int per_sm = 0, sms = 0;
-    LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    if (per_sm < 1) return fail(LDPC_E_UNSUPPORTED, "BP state of this code does not fit on one SM");
-    const long long want = (frames + F - 1) / F;
-    const long long grid = std::min<long long>((long long) per_sm * sms, want);
-    // frames are claimed from the global queue in chunks; small enough that the tail stays balanced
-    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * 4 * F) * F));
-    kernel<<<(unsigned) grid, threads, smem, stream>>>(p);
-    LDPC_CUDA(cudaGetLastError());
-    return LDPC_OK;
+static LrKernel lr_kernel_ft(bool soft) { return soft ? bp_lr_kernel<F, MAXT, true, false> : bp_lr_kernel<F, MAXT, false, false>; }
+
+// register budget by CTA size: 128 / 102 / 85 registers per thread; the generic-degree routines only at 128
+template <int F>
+static LrKernel lr_kernel_f(int threads, bool soft, bool wide) {
+    if (wide) return soft ? bp_lr_kernel<F, 512, true, true> : bp_lr_kernel<F, 512, false, true>;
+    if (threads <= 512) return lr_kernel_ft<F, 512>(soft);
+    if (threads <= 640) return lr_kernel_ft<F, 640>(soft);
+    return lr_kernel_ft<F, 768>(soft);
 }
 
-// testing hook: statistics of the shared-memory layout for F frames per CTA (ldpc_debug_bp_layout)
+static LrKernel lr_kernel(int F, int threads, bool soft, bool wide) {
+    switch (F) {
+        case 16: return lr_kernel_f<16>(threads, soft, wide);
+        case 8: return lr_kernel_f<8>(threads, soft, wide);
+        case 4: return lr_kernel_f<4>(threads, soft, wide);
+        default: return lr_kernel_f<2>(threads, soft, wide);
+    }
+}
+
+// testing hook: statistics of the shared-memory layout for F frames per team (ldpc_debug_bp_layout)
 int bp_lr_layout_stats(const ldpc_code *c, int F, int32_t out[6]) {
     if (F != 2 && F != 4 && F != 8 && F != 16) return fail(LDPC_E_INVALID, "F must be 2, 4, 8 or 16");
     BpLrSchedule s;
@@ -837,16 +898,6 @@ int bp_lr_layout_stats(const ldpc_code *c, int F, int32_t out[6]) {
     if (st) return st;
     out[0] = s.n_slots; out[1] = s.pad_even; out[2] = s.clash_v; out[3] = s.pairs_v; out[4] = s.clash_c; out[5] = s.pairs_c;
     return LDPC_OK;
-}
-
-// register budget by CTA size: 128 / 102 / 85 registers per thread
-template <int F>
-static int launch_lr_f(BpLrParams &p, const ldpc_code *c, int threads, int64_t frames, cudaStream_t stream) {
-    int maxt = threads <= 512 ? 512 : (threads <= 640 ? 640 : 768);
-    if (const char *force = getenv("LDPC_BP_MAXT")) maxt = std::max(maxt, atoi(force));
-    if (maxt <= 512) return launch_lr_ft<F, 512>(p, c, threads, frames, stream);
-    if (maxt <= 640) return launch_lr_ft<F, 640>(p, c, threads, frames, stream);
-    return launch_lr_ft<F, 768>(p, c, threads, frames, stream);
 }
 
 int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double var, int max_iter, int early_exit,
@@ -860,8 +911,9 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     io.counters = fio.counters; io.gen_cols = c->d.gen_cols; io.k = c->k; io.k_words = c->k_words;
     io.frames = frames; io.queue = queue; io.var = var; io.sigma = std::sqrt(var);
     io.n = c->n; io.m = c->m; io.row_ptr = c->d.row_ptr; io.col_idx = c->d.col_idx;
-    p.E = c->E; p.max_iter = max_iter; p.early_exit = early_exit;
-    p.soft = fio.soft != nullptr;
+    p.max_iter = max_iter; p.early_exit = early_exit;
+    const bool soft = fio.soft != nullptr, exp_mode = fio.experiment != 0;
+    const bool wide = std::max(c->max_row_deg, c->max_col_deg) > LR_MAX_UNROLLED;
     const double c1 = bp_lr_cap(c, &p.llr_cap);
     {
         const double lo = std::exp(-c1), hi = std::exp(c1);
@@ -871,39 +923,69 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
         p.clamp_lo = (int) (blo >> 32);
         p.clamp_hi = (int) (bhi >> 32);
     }
-    const bool exp_mode = fio.experiment != 0;
+    // Launch shape: ONE CTA per SM made of independent teams (F frames, `gt` threads, a named barrier and a region of
+    // shared memory each) that share the read-only tables.  Several small teams beat one large one: the FP64-bound check
+    // pass of one overlaps the shared-memory-bound variable pass of another, and a small team refills its frame slots
+    // sooner (profiles/r01_bp_lr_sweep.txt, when teams were CTAs: H05, fixed iterations: one CTA of 16 frames 50.5 ms, two
+    // of 8 45.6 ms, four of 4 45.6 ms).  Holding the tables once per SM makes room for a fifth team of 4 frames on the
+    // 160 x 280 codes (20 frames and 20 warps per SM instead of 16).
     const int rec_words = rec_words_of(c);
-    // Frames per CTA and CTAs per SM.  Several small CTAs per SM beat one large one: the FP64-bound check pass of one
-    // overlaps the shared-memory-bound variable pass of another, and a small CTA refills its frame slots sooner
-    // (profiles/r01_bp_lr_sweep.txt: H05, fixed iterations: one CTA of 16 frames 50.5 ms, two of 8 45.6 ms, four of 4
-    // 45.6 ms; as run at -3 dB 31.8 vs 31.0 ms for two / four; optimalH 47.6 vs 46.6 ms; (3,6)-1008: one CTA of 4 frames
-    // 48.8 ms, two of 2 46.0 ms before the layout annealing).  The kernel needs 128 registers per thread, i.e. 512 threads
-    // per SM: four CTAs of 4 frames x 128 threads where their messages fit, else two CTAs of the largest F that fits twice
-    // x 256 threads, else one CTA x 512 threads.
-    auto smem_of = [&](int f) { return lr_smem_bytes(c, c->E + c->m, f, p.soft, exp_mode, rec_words, 64 * 24); };
+    const int max_threads = wide ? 512 : 640;            // registers: 128 (generic-degree routines) / 102 per thread
+    auto gt_of = [&](int f) {
+        const int lanes = std::max(c->n, c->m) * (f / 2);
+        int gt = std::min(f <= 4 ? (f == 4 ? 128 : 256) : (f == 8 ? 256 : 512), std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
+        if (const char *force = getenv("LDPC_BP_THREADS")) {
+            const int v = atoi(force) / 32 * 32;
+            if (v >= 32 && v <= 768) gt = v;
+        }
+        return std::min(gt, max_threads);
+    };
+    auto teams_of = [&](int f) {          // teams of f frames that fit an SM (tables estimated from above: 24 step rows)
+        const size_t tables = (size_t) 4 * (rec_words + 24 * gt_of(f));
+        const size_t team = lr_team_bytes(c, c->E + c->m, f, soft, exp_mode, nullptr);
+        if (tables + team > LR_SMEM_MAX) return 0;
+        return (int) std::min<size_t>(std::min<size_t>(15, max_threads / gt_of(f)), (LR_SMEM_MAX - tables) / team);
+    };
     int F = 8;
     if (const char *force = getenv("LDPC_BP_F")) {
         const int v = atoi(force);
         if (v == 2 || v == 4 || v == 8 || v == 16) F = v;
     } else {
-        if (4 * smem_of(4) <= 227 * 1024) F = 4;
+        if (teams_of(4) >= 4) F = 4;
         while (F > 2 && frames < 2ll * 148 * F) F >>= 1;      // small batches: spread the frames over the SMs
-        while (F > 2 && 2 * smem_of(F) > 227 * 1024) F >>= 1;
+        while (F > 2 && teams_of(F) < 2) F >>= 1;
     }
-    while (F > 2 && smem_of(F) > 227 * 1024) F >>= 1;
-    const int lanes = std::max(c->n, c->m) * (F / 2);
-    const int ctas_per_sm = (int) std::min<size_t>(4, std::max<size_t>(1, (227 * 1024) / smem_of(F)));
-    int threads = std::min(ctas_per_sm >= 4 ? 128 : (ctas_per_sm >= 2 ? 256 : 512), std::max(64, (int) (lanes / 2.9 + 16) / 32 * 32));
-    if (const char *force = getenv("LDPC_BP_THREADS")) {
-        const int v = atoi(force) / 32 * 32;
-        if (v >= 32 && v <= 768) threads = v;
-    }
-    switch (F) {
-        case 16: return launch_lr_f<16>(p, c, threads, frames, stream);
-        case 8: return launch_lr_f<8>(p, c, threads, frames, stream);
-        case 4: return launch_lr_f<4>(p, c, threads, frames, stream);
-        default: return launch_lr_f<2>(p, c, threads, frames, stream);
-    }
+    while (F > 2 && teams_of(F) < 1) F >>= 1;
+    const int gt = gt_of(F);
+    BpLrSchedule s;
+    int st = get_lr_schedule(c, F, gt / 32, &s);
+    if (st) return st;
+    p.rec_v = s.rec_v; p.steps = s.steps; p.rec_words = s.rec_words; p.steps_c = s.steps_c; p.steps_v = s.steps_v;
+    p.var_store = s.var_store; p.E = s.n_slots;             // message slots including the idle ones
+    p.gt = gt;
+    const size_t tables = up16((size_t) 4 * (s.rec_words + (s.steps_c + s.steps_v) * gt));
+    const size_t team_bytes = lr_team_bytes(c, s.n_slots, F, soft, exp_mode, &p);
+    p.off_teams = (uint32_t) tables;
+    if (tables + team_bytes > LR_SMEM_MAX) return fail(LDPC_E_UNSUPPORTED, "BP messages of this code exceed 227 KB of shared memory");
+    int teams = (int) std::min<size_t>(std::min<size_t>(15, max_threads / gt), (LR_SMEM_MAX - tables) / team_bytes);
+    if (const char *force = getenv("LDPC_BP_TEAMS")) teams = std::max(1, std::min(teams, atoi(force)));
+    int sms = 0;
+    LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const long long want = (frames + F - 1) / F;            // teams the batch can keep busy
+    const long long grid = std::min<long long>(sms, want);
+    teams = (int) std::min<long long>(teams, (want + grid - 1) / grid);
+    const int threads = teams * gt;
+    const size_t smem = tables + (size_t) teams * team_bytes;
+    LrKernel kernel = lr_kernel(F, threads, soft, wide);
+    LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int per_sm = 0;
+    LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(LDPC_E_UNSUPPORTED, "BP state of this code does not fit on one SM");
+    // frames are claimed from the global queue in chunks; small enough that the tail stays balanced
+    p.chunk = (int) std::max<long long>(1, std::min<long long>(F, frames / (grid * teams * 4 * F) * F));
+    kernel<<<(unsigned) grid, threads, smem, stream>>>(p);
+    LDPC_CUDA(cudaGetLastError());
+    return LDPC_OK;
 }
 
 }  // namespace ldpc

@@ -50,9 +50,9 @@ struct BpSchedule {   // device arrays, rounds x warps jobs each (log-domain ker
 // likelihood-ratio BP kernel (bp_lr_kernel.cu): tables depend on the frames per CTA (byte offsets are pre-scaled)
 struct BpLrSchedule {
     uint32_t *rec_v = nullptr;    // variable node records
-    uint32_t *steps = nullptr;    // per warp: variable-pass steps, check-pass steps (bp_lr_kernel.cu: lr_step_word)
+    uint32_t *steps = nullptr;    // one word per (step row, thread of a team): check-pass rows, then variable-pass rows (lr_step_word)
     uint16_t *var_store = nullptr; // variable index -> storage index of its per-variable arrays
-    int rec_words = 0, steps_per_warp = 0, steps_c_off = 0, n_slots = 0, pad_even = 0;
+    int rec_words = 0, steps_c = 0, steps_v = 0, n_slots = 0, pad_even = 0;
     int clash_v = 0, pairs_v = 0, clash_c = 0, pairs_c = 0;   // layout statistics (ldpc_debug_bp_layout)
 };
 
@@ -119,7 +119,7 @@ struct ldpc_code {
     std::vector<ldpc::BpClass> chk_classes, var_classes;   // nodes of equal degree are adjacent in rank order
     std::vector<int> chk_order, var_order;                 // rank -> node index (degree-0 nodes dropped)
     ldpc::DeviceTables d;
-    // BP launch schedules, built on first use per (frames per CTA, warps per CTA)
+    // BP launch schedules, built on first use per (frames per CTA or team, warps per CTA or team)
     mutable std::mutex sched_mu;
     mutable std::map<std::pair<int, int>, ldpc::BpSchedule> bp_sched;
     mutable std::map<std::pair<int, int>, ldpc::BpLrSchedule> bp_lr_sched;

@@ -37,6 +37,9 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
 __device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short) v) : "memory");
+}
 
 }  // namespace ldpc
 
