@@ -129,12 +129,14 @@ __device__ __forceinline__ double clamp_sign(double x, int neg_lo, int range, in
 struct LrAddr {
     uint32_t msg, dec;          // messages (L_ch: + off_lch, posteriors: + off_post, both uniform), decisions
     uint32_t off_lch, off_post;
+    uint32_t rec;               // the record table
+    int neg_lo, range, lo;      // clamp constants: -hi word of exp(-C1), hi(exp(C1)) - hi(exp(-C1)), hi word of exp(-C1)
 };
 
 // ---- variable node of degree D, two frames: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
 // rec = shared-window address of the node's record
 template <int D, bool SOFT>
-__device__ __forceinline__ void lr_var_update(const LrAddr &A, uint32_t rec, int d_runtime, int clamp_lo, int clamp_hi) {
+__device__ __forceinline__ void lr_var_update(const LrAddr &A, uint32_t rec, int d_runtime) {
     const int d = D > 0 ? D : d_runtime;
     constexpr int CAP = D > 0 ? D : LR_MAX_DEGREE;
     uint32_t w[CAP + 4];
@@ -162,8 +164,8 @@ __device__ __forceinline__ void lr_var_update(const LrAddr &A, uint32_t rec, int
     }
     const P2 tot = lam[d - 1] * x[d - 1];       // posterior likelihood ratios
     const bool one_a = tot.a <= 1.0, one_b = tot.b <= 1.0;   // estimate <= 0 -> bit 1 (bp.h:193)
-    const int sa = clamp_lo + (one_a ? (int) 0x80000000 : 0), sb = clamp_lo + (one_b ? (int) 0x80000000 : 0);
-    const int neg_lo = -clamp_lo, range = clamp_hi - clamp_lo;
+    const int sa = A.lo + (one_a ? (int) 0x80000000 : 0), sb = A.lo + (one_b ? (int) 0x80000000 : 0);
+    const int neg_lo = A.neg_lo, range = A.range;
 #pragma unroll
     for (int j = 0; j < d; ++j)
         st_p2(A.msg + w[1 + j], P2{clamp_sign(lam[j].a, neg_lo, range, sa), clamp_sign(lam[j].b, neg_lo, range, sb)});
@@ -254,7 +256,33 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     LrShared<F> *L = reinterpret_cast<LrShared<F> *>(base + p.off_ctl);
     SlotBlock<F> *S = &L->S;
 
-    team_slots_init(T, S);
+    // shared-window addresses of this lane's share
+    // (They take a round trip through shared memory: a value ptxas can derive from the thread index is recomputed at
+    // every step instead of being kept -- fourteen instructions per step; a loaded value stays in its register.)
+    LrAddr A;
+    {
+        const uint32_t scratch = smem_addr(msg) + tid * 32;
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "r"(smem_addr(msg) + pair * 16),
+                     "r"(smem_addr(dec) + pair * 2), "r"(smem_addr(steps) + tid * 4), "r"(2u * pair) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(scratch + 16), "r"(smem_addr(rec)), "r"(-p.clamp_lo),
+                     "r"(p.clamp_hi - p.clamp_lo), "r"(p.clamp_lo) : "memory");
+    }
+    T.sync();
+    const uint4 kept = lds_u32x4(smem_addr(msg) + tid * 32), kept2 = lds_u32x4(smem_addr(msg) + tid * 32 + 16);
+    T.sync();
+    A.msg = kept.x;
+    A.dec = kept.y;
+    A.off_lch = p.off_lch;
+    A.off_post = p.off_post;
+    A.rec = kept2.x;
+    A.neg_lo = (int) kept2.y;
+    A.range = (int) kept2.z;
+    A.lo = (int) kept2.w;
+    const uint32_t a_steps_c = kept.z, a_steps_v = a_steps_c + p.steps_c * gt * 4;
+    const uint32_t row = (uint32_t) gt * 4;
+    const unsigned pair_shift = kept.w, pair_bits = 3u << pair_shift;
+
+    team_slots_init(T, S);                      // (after the round trip: its scratch may reach into the control block)
     if (tid == 0) {
         L->ctl[0] = LrCtl{0u, 0u, 0u, 0u};
         L->ctl[1] = LrCtl{0u, 0u, 0u, 0u};
@@ -264,26 +292,6 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
         S->alive = F;
     }
     __syncthreads();                            // the only CTA-wide barrier: tables are in place
-
-    // shared-window addresses of this lane's share
-    // (They take a round trip through shared memory: a value ptxas can derive from the thread index is recomputed at
-    // every step instead of being kept -- fourteen instructions per step; a loaded value stays in its register.)
-    LrAddr A;
-    {
-        const uint32_t scratch = smem_addr(msg) + tid * 16;
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "r"(smem_addr(msg) + pair * 16),
-                     "r"(smem_addr(dec) + pair * 2), "r"(smem_addr(steps) + tid * 4), "r"(2u * pair) : "memory");
-    }
-    T.sync();
-    const uint4 kept = lds_u32x4(smem_addr(msg) + tid * 16);
-    T.sync();
-    A.msg = kept.x;
-    A.dec = kept.y;
-    A.off_lch = p.off_lch;
-    A.off_post = p.off_post;
-    const uint32_t a_steps_c = kept.z, a_steps_v = a_steps_c + p.steps_c * gt * 4;
-    const uint32_t a_rec = smem_addr(rec), row = (uint32_t) gt * 4;
-    const unsigned pair_shift = kept.w, pair_bits = 3u << pair_shift;
 
     for (unsigned trip = 0;; ++trip) {
         LrCtl *ctl = &L->ctl[trip & 1];
@@ -406,14 +414,14 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
             if (WIDE) {
                 while (e >= ((uint32_t) (LR_MAX_UNROLLED + 1) << 24)) {
                     const uint32_t nx = lds_u32(q += row);
-                    if (!(e & LR_STEP_IDLE)) lr_var_update<0, SOFT>(A, a_rec + (e & LR_STEP_OFF), (int) (e >> 24), p.clamp_lo, p.clamp_hi);
+                    if (!(e & LR_STEP_IDLE)) lr_var_update<0, SOFT>(A, A.rec + (e & LR_STEP_OFF), (int) (e >> 24));
                     e = nx;
                 }
             }
 #define LDPC_VAR_STEPS(D)                                                                                         \
     while (e >= ((uint32_t) (D) << 24)) {                                                                         \
         const uint32_t nx = lds_u32(q += row);                                                                    \
-        if (!(e & LR_STEP_IDLE)) lr_var_update<D, SOFT>(A, a_rec + e - ((uint32_t) (D) << 24), D, p.clamp_lo, p.clamp_hi); \
+        if (!(e & LR_STEP_IDLE)) lr_var_update<D, SOFT>(A, A.rec + e - ((uint32_t) (D) << 24), D);           \
         e = nx;                                                                                                   \
     }
             LDPC_VAR_STEPS(8) LDPC_VAR_STEPS(7) LDPC_VAR_STEPS(6) LDPC_VAR_STEPS(5)
@@ -437,7 +445,7 @@ static size_t lr_team_bytes(const ldpc_code *c, int n_slots, int F, bool soft, b
     const size_t off_post = off; off += soft ? (size_t) c->n * F * 8 : 0;
     const size_t off_dec = off; off += (size_t) c->n * F;
     const size_t off_cw = off; off += experiment ? (size_t) c->n * F : 0;
-    const size_t off_ctl = up16(off); off = up16(off_ctl + sizeof(LrShared<16>));
+    const size_t off_ctl = up16(off); off = std::max<size_t>(up16(off_ctl + sizeof(LrShared<16>)), 768 * 32);   // >= the kernel's start-up scratch
     if (p) {
         p->off_lch = (uint32_t) off_lch; p->off_post = (uint32_t) off_post; p->off_dec = (uint32_t) off_dec;
         p->off_cw = (uint32_t) off_cw; p->off_ctl = (uint32_t) off_ctl; p->team_bytes = (uint32_t) off;

@@ -122,16 +122,17 @@ __device__ __forceinline__ double log_pos(double x) {
     return x >= 1.0 ? log_ratio(x, 1.0) : -log_ratio(1.0, x);
 }
 
-// a / b for positive normal a, b with b in [2^-1000, 2^1000]: MUFU seed, one Newton step on the
-// reciprocal, quotient, one residual correction (error <= ~1 ulp, no special cases)
+// a / b for positive normal a, b with b in [2^-1000, 2^1000], four FP64 instructions behind the MUFU seed:
+//   r0 = 1/b (1 - e) with |e| <= 2^-22 (MUFU.RCP64H), so a/b = a r0 / (1 - e) = q0 (1 + e + e^2 + e^3 + ...);
+//   q = q0 + q0 (e + e^2) drops e^3 <= 2^-66 and carries the roundings of q0 and of the final fma: ~1 ulp, no special cases.
+// (The Newton form -- refine r, multiply, correct the quotient's residual -- takes five.)
 __device__ __forceinline__ double div_pos(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double q0 = a * r;
     const double e = __fma_rn(-b, r, 1.0);
-    r = __fma_rn(r, e, r);
-    const double q = a * r;
-    const double rem = __fma_rn(-b, q, a);
-    return __fma_rn(rem, r, q);
+    const double e2 = __fma_rn(e, e, e);
+    return __fma_rn(q0, e2, q0);
 }
 
 }  // namespace ldpc
