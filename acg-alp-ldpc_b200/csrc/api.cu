@@ -6,8 +6,14 @@
 // code handle can be shared by any number of threads.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
+#include <mutex>
+#include <string>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "ldpc_internal.h"
 
@@ -155,6 +161,77 @@ int decode_host(const ldpc_code *c, const DecodeCfg &cfg, const double *y, int64
     return LDPC_OK;
 }
 
+// ---- one Monte-Carlo shard: checks, launch (asynchronous, counters stay on the device), collection
+
+int experiment_check(const ldpc_code *c, const ldpc_algo_cfg_t *cfg, int codeword_source, const uint8_t *words, uint64_t n_words) {
+    if (!c || !cfg) return fail(LDPC_E_INVALID, "NULL argument");
+    if (cfg->algo != LDPC_ALGO_BP && cfg->algo != LDPC_ALGO_QPADMM) return fail(LDPC_E_INVALID, "unknown algo");
+    if (cfg->max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
+    if (codeword_source < LDPC_CW_ZERO || codeword_source > LDPC_CW_GENERATOR)
+        return fail(LDPC_E_INVALID, "unknown codeword source");
+    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
+        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
+    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
+        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
+    return LDPC_OK;
+}
+
+struct ExperimentJob {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    unsigned long long *counters = nullptr;      // the calling thread's per-device counter block (device memory)
+    uint8_t *d_words = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+int experiment_enqueue(const ldpc_code *c, const ldpc_algo_cfg_t *cfg, double snr, uint64_t seed, uint64_t frame_begin,
+                       uint64_t frame_count, int codeword_source, const uint8_t *words, uint64_t n_words, ExperimentJob *job) {
+    LDPC_CUDA(cudaSetDevice(c->device));
+    DecodeCfg dc{cfg->algo, snr, cfg->alpha, cfg->mu, cfg->eps_stop, cfg->max_iter, cfg->early_exit};
+    Slot &s = g_ctx.per_device[c->device][0];
+    int st = slot_init(s);
+    if (st) return st;
+    job->device = c->device;
+    job->stream = s.stream;
+    job->counters = s.counters;
+    if (codeword_source == LDPC_CW_TABLE) {
+        LDPC_CUDA(cudaMalloc((void **) &job->d_words, n_words * (size_t) c->n));
+        LDPC_CUDA(cudaMemcpyAsync(job->d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream));
+    }
+    LDPC_CUDA(cudaEventCreate(&job->e0));
+    LDPC_CUDA(cudaEventCreate(&job->e1));
+    LDPC_CUDA(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * LDPC_CNT_COUNT, s.stream));
+    FrameIO io;
+    io.experiment = 1; io.seed = seed; io.frame_begin = frame_begin; io.cw_source = codeword_source;
+    io.words = job->d_words; io.n_words = n_words; io.counters = s.counters;
+    LDPC_CUDA(cudaEventRecord(job->e0, s.stream));
+    if (frame_count > 0) st = enqueue_decode(c, dc, io, (int64_t) frame_count, s.queue, s.stream);
+    LDPC_CUDA(cudaEventRecord(job->e1, s.stream));
+    return st;
+}
+
+// waits for the shard's stream and reads its counter block (also after a failed enqueue: the stream is drained)
+int experiment_collect(ExperimentJob *job, uint64_t counters[LDPC_CNT_COUNT], double *gpu_seconds) {
+    LDPC_CUDA(cudaSetDevice(job->device));
+    unsigned long long host_cnt[LDPC_CNT_COUNT];
+    LDPC_CUDA(cudaMemcpyAsync(host_cnt, job->counters, sizeof(host_cnt), cudaMemcpyDeviceToHost, job->stream));
+    LDPC_CUDA(cudaStreamSynchronize(job->stream));
+    for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = host_cnt[i];
+    float ms = 0;
+    if (job->e0 && job->e1 && cudaEventElapsedTime(&ms, job->e0, job->e1) == cudaSuccess && gpu_seconds) *gpu_seconds = ms * 1e-3;
+    cudaGetLastError();
+    return LDPC_OK;
+}
+
+void experiment_release(ExperimentJob *job) {
+    if (job->stream) { cudaSetDevice(job->device); cudaStreamSynchronize(job->stream); }
+    if (job->e0) cudaEventDestroy(job->e0);
+    if (job->e1) cudaEventDestroy(job->e1);
+    cudaFree(job->d_words);
+    cudaGetLastError();
+    *job = ExperimentJob();
+}
+
 }  // namespace
 
 extern "C" {
@@ -246,56 +323,208 @@ int ldpc_generator_codewords(const ldpc_code_t *c, uint64_t seed, uint64_t frame
 int ldpc_experiment_run(const ldpc_code_t *c, const ldpc_algo_cfg_t *cfg, double snr, uint64_t seed,
                         uint64_t frame_begin, uint64_t frame_count, int32_t codeword_source, const uint8_t *words,
                         uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT], double *gpu_seconds) {
-    if (!c || !cfg || !counters) return fail(LDPC_E_INVALID, "NULL argument");
-    if (cfg->algo != LDPC_ALGO_BP && cfg->algo != LDPC_ALGO_QPADMM) return fail(LDPC_E_INVALID, "unknown algo");
-    if (cfg->max_iter < 0) return fail(LDPC_E_INVALID, "max_iter < 0");
-    if (codeword_source == LDPC_CW_TABLE && (!words || n_words == 0))
-        return fail(LDPC_E_INVALID, "LDPC_CW_TABLE needs a codeword table");
-    if (codeword_source == LDPC_CW_GENERATOR && (c->k <= 0 || !c->d.gen_cols))
-        return fail(LDPC_E_INVALID, "LDPC_CW_GENERATOR needs ldpc_code_set_generator");
-    if (codeword_source < LDPC_CW_ZERO || codeword_source > LDPC_CW_GENERATOR)
-        return fail(LDPC_E_INVALID, "unknown codeword source");
-    LDPC_CUDA(cudaSetDevice(c->device));
+    if (!counters) return fail(LDPC_E_INVALID, "NULL argument");
+    int st = experiment_check(c, cfg, codeword_source, words, n_words);
+    if (st) return st;
     for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = 0;
     if (gpu_seconds) *gpu_seconds = 0.0;
     if (frame_count == 0) return LDPC_OK;
-
-    DecodeCfg dc{cfg->algo, snr, cfg->alpha, cfg->mu, cfg->eps_stop, cfg->max_iter, cfg->early_exit};
-    Slot &s = g_ctx.per_device[c->device][0];
-    int st = slot_init(s);
-    if (st) return st;
-    uint8_t *d_words = nullptr;
-    if (codeword_source == LDPC_CW_TABLE) {
-        LDPC_CUDA(cudaMalloc((void **) &d_words, n_words * (size_t) c->n));
-        cudaError_t e = cudaMemcpyAsync(d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream);
-        if (e != cudaSuccess) { cudaFree(d_words); return cuda_fail(e, "codeword table upload", __FILE__, __LINE__); }
-    }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * LDPC_CNT_COUNT, s.stream);
-    FrameIO io;
-    io.experiment = 1; io.seed = seed; io.frame_begin = frame_begin; io.cw_source = codeword_source;
-    io.words = d_words; io.n_words = n_words; io.counters = s.counters;
-    cudaEventRecord(e0, s.stream);
-    st = enqueue_decode(c, dc, io, (int64_t) frame_count, s.queue, s.stream);
-    cudaEventRecord(e1, s.stream);
-    unsigned long long host_cnt[LDPC_CNT_COUNT];
-    if (!st) {
-        cudaError_t e = cudaMemcpyAsync(host_cnt, s.counters, sizeof(host_cnt), cudaMemcpyDeviceToHost, s.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        if (e != cudaSuccess) st = cuda_fail(e, "experiment", __FILE__, __LINE__);
-    }
-    if (!st) {
-        for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = host_cnt[i];
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (gpu_seconds) *gpu_seconds = ms * 1e-3;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d_words);
+    ExperimentJob job;
+    st = experiment_enqueue(c, cfg, snr, seed, frame_begin, frame_count, codeword_source, words, n_words, &job);
+    if (!st) st = experiment_collect(&job, counters, gpu_seconds);
+    experiment_release(&job);
     return st;
+}
+
+// ---- multi-GPU: NCCL through dlopen (the library has no link-time dependency on it)
+
+namespace {
+
+struct Nccl {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+Nccl &nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // inside a torch process the bundled libnccl.so.2 is already loaded and this returns it
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        if (!n.lib) return;
+        auto sym = [&](const char *name) { return dlsym(n.lib, name); };
+        n.GetUniqueId = (decltype(n.GetUniqueId)) sym("ncclGetUniqueId");
+        n.CommInitRank = (decltype(n.CommInitRank)) sym("ncclCommInitRank");
+        n.CommInitAll = (decltype(n.CommInitAll)) sym("ncclCommInitAll");
+        n.AllReduce = (decltype(n.AllReduce)) sym("ncclAllReduce");
+        n.CommDestroy = (decltype(n.CommDestroy)) sym("ncclCommDestroy");
+        n.GroupStart = (decltype(n.GroupStart)) sym("ncclGroupStart");
+        n.GroupEnd = (decltype(n.GroupEnd)) sym("ncclGroupEnd");
+        n.GetErrorString = (decltype(n.GetErrorString)) sym("ncclGetErrorString");
+        n.ok = n.GetUniqueId && n.CommInitRank && n.CommInitAll && n.AllReduce && n.CommDestroy && n.GroupStart && n.GroupEnd &&
+               n.GetErrorString;
+    });
+    return n;
+}
+
+int nccl_fail(ncclResult_t r, const char *what) {
+    return fail(LDPC_E_CUDA, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error"));
+}
+
+#define LDPC_NCCL(call)                                         \
+    do {                                                        \
+        ncclResult_t r__ = (call);                              \
+        if (r__ != ncclSuccess) return nccl_fail(r__, #call);   \
+    } while (0)
+
+// single-process communicators, one per device list (ncclCommInitAll is expensive: 0.1-1 s)
+struct CommSet {
+    std::vector<ncclComm_t> comms;
+};
+std::mutex g_comm_mu;
+std::map<std::vector<int>, CommSet> g_comm_sets;
+
+}  // namespace
+
+struct ldpc_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    unsigned long long *buf = nullptr;
+    size_t cap = 0;
+};
+
+int ldpc_experiment_run_multi(const ldpc_code_t *const *codes, int32_t n_devices, const ldpc_algo_cfg_t *cfg, double snr,
+                              uint64_t seed, uint64_t frame_begin, uint64_t frame_count, int32_t codeword_source,
+                              const uint8_t *words, uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT],
+                              double *gpu_seconds) {
+    if (!codes || n_devices < 1 || !counters) return fail(LDPC_E_INVALID, "bad argument");
+    std::vector<int> devices;
+    for (int g = 0; g < n_devices; ++g) {
+        int st = experiment_check(codes[g], cfg, codeword_source, words, n_words);
+        if (st) return st;
+        if (codes[g]->n != codes[0]->n || codes[g]->m != codes[0]->m || codes[g]->E != codes[0]->E)
+            return fail(LDPC_E_INVALID, "the code handles of ldpc_experiment_run_multi must describe the same H");
+        for (int d : devices)
+            if (d == codes[g]->device) return fail(LDPC_E_INVALID, "two code handles on one device");
+        devices.push_back(codes[g]->device);
+    }
+    for (int i = 0; i < LDPC_CNT_COUNT; ++i) counters[i] = 0;
+    if (gpu_seconds) *gpu_seconds = 0.0;
+    if (frame_count == 0) return LDPC_OK;
+    if (n_devices == 1)
+        return ldpc_experiment_run(codes[0], cfg, snr, seed, frame_begin, frame_count, codeword_source, words, n_words, counters,
+                                   gpu_seconds);
+    Nccl &nc = nccl();
+    if (!nc.ok) return fail(LDPC_E_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    CommSet *set = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_comm_mu);
+        auto it = g_comm_sets.find(devices);
+        if (it == g_comm_sets.end()) {
+            CommSet cs;
+            cs.comms.resize(n_devices);
+            LDPC_NCCL(nc.CommInitAll(cs.comms.data(), n_devices, devices.data()));
+            it = g_comm_sets.emplace(devices, cs).first;
+        }
+        set = &it->second;
+    }
+    // all shards are enqueued from this thread (launches are asynchronous), then one grouped all-reduce on the shards' streams
+    std::vector<ExperimentJob> jobs(n_devices);
+    int st = LDPC_OK;
+    for (int g = 0; g < n_devices && !st; ++g) {
+        const uint64_t b = frame_count * (uint64_t) g / (uint64_t) n_devices, e = frame_count * (uint64_t) (g + 1) / (uint64_t) n_devices;
+        st = experiment_enqueue(codes[g], cfg, snr, seed, frame_begin + b, e - b, codeword_source, words, n_words, &jobs[g]);
+    }
+    if (!st) {
+        std::lock_guard<std::mutex> lock(g_comm_mu);        // one collective at a time per communicator set
+        ncclResult_t r = nc.GroupStart();
+        for (int g = 0; g < n_devices && r == ncclSuccess; ++g)
+            r = nc.AllReduce(jobs[g].counters, jobs[g].counters, LDPC_CNT_COUNT, ncclUint64, ncclSum, set->comms[g], jobs[g].stream);
+        const ncclResult_t r2 = nc.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess) st = nccl_fail(r != ncclSuccess ? r : r2, "ncclAllReduce of the counter blocks");
+    }
+    uint64_t tmp[LDPC_CNT_COUNT];
+    double longest = 0.0;
+    for (int g = 0; g < n_devices; ++g) {                   // every stream is drained, also after a failure
+        double secs = 0.0;
+        const int sg = jobs[g].stream ? experiment_collect(&jobs[g], g == 0 ? counters : tmp, &secs) : LDPC_OK;
+        if (!st) st = sg;
+        longest = std::max(longest, secs);
+        experiment_release(&jobs[g]);
+    }
+    if (gpu_seconds) *gpu_seconds = longest;
+    return st;
+}
+
+int ldpc_comm_unique_id(uint8_t id[LDPC_COMM_ID_BYTES]) {
+    if (!id) return fail(LDPC_E_INVALID, "NULL argument");
+    Nccl &nc = nccl();
+    if (!nc.ok) return fail(LDPC_E_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == LDPC_COMM_ID_BYTES, "NCCL id size");
+    ncclUniqueId u;
+    LDPC_NCCL(nc.GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return LDPC_OK;
+}
+
+int ldpc_comm_init(int32_t rank, int32_t world, const uint8_t id[LDPC_COMM_ID_BYTES], int device, ldpc_comm_t **out) {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(LDPC_E_INVALID, "bad argument");
+    Nccl &nc = nccl();
+    if (!nc.ok) return fail(LDPC_E_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    LDPC_CUDA(cudaSetDevice(device));
+    ldpc_comm *c = new ldpc_comm;
+    c->device = device;
+    c->world = world;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclResult_t r = nc.CommInitRank(&c->comm, world, u, rank);
+    if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { nc.CommDestroy(c->comm); delete c; return cuda_fail(e, "stream", __FILE__, __LINE__); }
+    *out = c;
+    return LDPC_OK;
+}
+
+int ldpc_allreduce_counters(ldpc_comm_t *c, uint64_t *counters, int32_t count) {
+    if (!c || !counters || count < 0) return fail(LDPC_E_INVALID, "bad argument");
+    if (count == 0) return LDPC_OK;
+    Nccl &nc = nccl();
+    LDPC_CUDA(cudaSetDevice(c->device));
+    if ((size_t) count > c->cap) {
+        cudaFree(c->buf);
+        c->buf = nullptr;
+        c->cap = 0;
+        LDPC_CUDA(cudaMalloc((void **) &c->buf, sizeof(unsigned long long) * (size_t) count));
+        c->cap = (size_t) count;
+    }
+    LDPC_CUDA(cudaMemcpyAsync(c->buf, counters, sizeof(uint64_t) * (size_t) count, cudaMemcpyHostToDevice, c->stream));
+    LDPC_NCCL(nc.AllReduce(c->buf, c->buf, (size_t) count, ncclUint64, ncclSum, c->comm, c->stream));
+    LDPC_CUDA(cudaMemcpyAsync(counters, c->buf, sizeof(uint64_t) * (size_t) count, cudaMemcpyDeviceToHost, c->stream));
+    LDPC_CUDA(cudaStreamSynchronize(c->stream));
+    return LDPC_OK;
+}
+
+void ldpc_comm_destroy(ldpc_comm_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
+    cudaFree(c->buf);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
 }
 
 int ldpc_qpadmm_grid_run(const ldpc_code_t *c, int32_t points, const double *alpha, const double *mu,

@@ -5,8 +5,8 @@
 // For a GpuDecoder the whole point -- codeword selection, AWGN, decoding, verdict
 // and counting -- runs on the GPUs: frames are sharded over the visible devices
 // by GLOBAL frame index (any device count yields the same frames), each device
-// returns one counter block, and the blocks are summed (the reference's
-// merge_exp_results after pthread_join).  Noise comes from the device Philox
+// produces one counter block, and the blocks are all-reduced over NVLink by NCCL
+// (ldpc_experiment_run_multi; the reference's merge_exp_results after pthread_join).  Noise comes from the device Philox
 // stream instead of mt19937(frame index + 1), so FER agrees with the reference
 // statistically, not frame by frame; decoder parity is checked on identical y
 // through Decoder::decode / the C ABI (tests/).
@@ -128,26 +128,22 @@ inline ExperimentResult gpu_experiment(const GpuDecoder &decoder, const vector<T
             die("ldpc_experiment_run");
         return from_counters(cnt, secs);
     }
+    // several GPUs: shards by global frame index, counter blocks all-reduced over NVLink by NCCL inside the library
+    // (the reference's merge_exp_results after pthread_join, experiment.h:70-78, 133-137)
     const int gpus = max(1, min<int>(visible_gpus(), (int) max<size_t>(frames, 1)));
     const ldpc_algo_cfg_t cfg = decoder.config();
-    const uint64_t seed = experiment_seed();
-    vector<ExperimentResult> parts(gpus, ExperimentResult(HammingDistanceTracker()));
-    vector<thread> workers;
-    for (int g = 0; g < gpus; ++g)
-        workers.emplace_back([&, g] {
-            const uint64_t begin = frames * g / gpus, end = frames * (g + 1) / gpus;
-            CodeRef code = CodeCache::instance().get(H, g);
-            uint64_t cnt[LDPC_CNT_COUNT];
-            double secs = 0;
-            if (ldpc_experiment_run(code.get(), &cfg, snr, seed, begin, end - begin, LDPC_CW_TABLE, words.data(), frames, cnt,
-                                    &secs) != LDPC_OK)
-                die("ldpc_experiment_run");
-            parts[g] = from_counters(cnt, secs);
-        });
-    for (thread &w : workers) w.join();
-    ExperimentResult total{HammingDistanceTracker()};
-    for (const ExperimentResult &p : parts) merge_exp_results(total, p);
-    return total;
+    vector<CodeRef> codes;
+    vector<const ldpc_code_t *> handles;
+    for (int g = 0; g < gpus; ++g) {
+        codes.push_back(CodeCache::instance().get(H, g));
+        handles.push_back(codes.back().get());
+    }
+    uint64_t cnt[LDPC_CNT_COUNT];
+    double secs = 0;
+    if (ldpc_experiment_run_multi(handles.data(), gpus, &cfg, snr, experiment_seed(), 0, frames, LDPC_CW_TABLE, words.data(),
+                                  frames, cnt, &secs) != LDPC_OK)
+        die("ldpc_experiment_run_multi");
+    return from_counters(cnt, secs);
 }
 
 // The (alpha, mu) double loop of qpadmm_params.cpp:51-67 in one launch per GPU: the parameter pairs are

@@ -70,6 +70,13 @@ def lib():
     L.ldpc_experiment_run.argtypes = [vp, C.POINTER(AlgoCfg), dbl, u64, u64, u64, i32, vp, u64, vp,
                                       C.POINTER(dbl)]
     L.ldpc_qpadmm_grid_run.argtypes = [vp, i32, vp, vp, i32, dbl, dbl, u64, u64, u64, i32, vp, u64, vp, C.POINTER(dbl)]
+    L.ldpc_experiment_run_multi.argtypes = [vp, i32, C.POINTER(AlgoCfg), dbl, u64, u64, u64, i32, vp, u64, vp,
+                                            C.POINTER(dbl)]
+    L.ldpc_comm_unique_id.argtypes = [vp]
+    L.ldpc_comm_init.argtypes = [i32, i32, vp, C.c_int, C.POINTER(vp)]
+    L.ldpc_allreduce_counters.argtypes = [vp, vp, i32]
+    L.ldpc_comm_destroy.argtypes = [vp]
+    L.ldpc_comm_destroy.restype = None
     L.ldpc_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.ldpc_host_free.argtypes = [vp]
     L.ldpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
@@ -125,6 +132,65 @@ def last_qpadmm_kernel():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+DATA = os.path.join(HERE, "data")
+
+
+def load_rows(name):
+    """Dense uint8 parity-check matrix from acg-alp-ldpc_b200/data/<name>.rows (the sparse text format the repo ships
+    its matrices in: '#' comments, "m n", then "deg c0 c1 ..." per row; utils/parse_data.h: read_pcm_rows)."""
+    lines = [l for l in open(os.path.join(DATA, name + ".rows")) if not l.startswith("#")]
+    m, n = (int(x) for x in lines[0].split())
+    H = np.zeros((m, n), np.uint8)
+    for r, line in enumerate(lines[1:1 + m]):
+        vals = [int(x) for x in line.split()]
+        assert vals[0] == len(vals) - 1
+        H[r, vals[1:]] = 1
+    return H
+
+
+class Comm:
+    """One rank of the path's only collective: the all-reduce of the counter blocks, done by the library's
+    own NCCL communicator.  `make_id()` on rank 0, hand the 128 bytes to every rank, then Comm(rank, world, id, device)."""
+
+    @staticmethod
+    def make_id():
+        buf = np.zeros(128, np.uint8)
+        _check(lib().ldpc_comm_unique_id(buf.ctypes.data))
+        return buf
+
+    def __init__(self, rank, world, comm_id, device=0):
+        self._h = C.c_void_p()
+        comm_id = np.ascontiguousarray(comm_id, np.uint8)
+        assert comm_id.size == 128
+        _check(lib().ldpc_comm_init(rank, world, comm_id.ctypes.data, device, C.byref(self._h)))
+
+    def allreduce(self, counters):
+        """sum of a dict (or array) of unsigned 64-bit counters over all ranks"""
+        keys = sorted(counters) if isinstance(counters, dict) else None
+        vec = np.array([counters[k] for k in keys] if keys else counters, np.uint64)
+        _check(lib().ldpc_allreduce_counters(self._h, vec.ctypes.data, vec.size))
+        return dict(zip(keys, (int(x) for x in vec))) if keys else vec
+
+    def close(self):
+        if self._h:
+            lib().ldpc_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def experiment_multi(codes, decoder, snr, seed, frame_begin, frame_count, source=CW_ZERO, words=None):
+    """ldpc_experiment_run_multi: one Monte-Carlo point sharded over the devices of `codes` (handles of the same H)"""
+    cfg = decoder.cfg()
+    cnt = np.zeros(len(CNT_NAMES), np.uint64)
+    secs = C.c_double()
+    w = None if words is None else np.ascontiguousarray(words, np.uint8)
+    handles = (C.c_void_p * len(codes))(*[c._h for c in codes])
+    _check(lib().ldpc_experiment_run_multi(handles, len(codes), C.byref(cfg), snr, seed, frame_begin, frame_count, source,
+                                           _ptr(w), 0 if w is None else w.shape[0], cnt.ctypes.data, C.byref(secs)))
+    res = dict(zip(CNT_NAMES, (int(x) for x in cnt)))
+    res["gpu_seconds"] = secs.value
+    return res
 
 
 class Code:

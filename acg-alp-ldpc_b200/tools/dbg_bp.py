@@ -1,7 +1,7 @@
 import os, sys, numpy as np
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/acg-alp-ldpc_b200')
 import ldpc_b200 as L
-from tests.helpers import load_rows
+from ldpc_b200 import load_rows
 for name in ("optimalH", "H05", "reg_3_6_1008"):
     code = L.Code(H=load_rows(name))
     for frames in (301, 6000):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import ldpc_b200 as L  # noqa: E402
-from tests.helpers import load_rows  # noqa: E402
+from ldpc_b200 import load_rows  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--algo", default="bp")

@@ -4,7 +4,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import ldpc_b200 as L
-from tests.helpers import load_rows
+from ldpc_b200 import load_rows
 H = load_rows("optimalH")
 rng = np.random.default_rng(1)
 dec = L.QPADMMDecoder(1.95, 0.5, 1000, 1e-5)

@@ -13,9 +13,17 @@ arm does the same work on the same kind of input.  QP-ADMM (optimalH, 1000 fixed
 iterations, eps_stop = 0) is measured in the same run and reported under "qpadmm"; both decoders on the
 synthetic (3,6)-regular n = 1008 code (configs[3]) under "reg_3_6_1008".
 
-One JSON line on stdout (rank 0).  Keys follow the driver's contract; the
-roofline is the FP64 pipe (messages never leave the SM, so HBM traffic is ~0.1 %
-of peak -- reported under roofline.hbm for completeness).
+Also in the line: BP on optimalH, QP-ADMM at main.cpp's 10000 iterations, the decoders as
+they really run (experiment mode, early exit, -3 dB and 0 dB, mean iterations), the channel
+kernel against the HBM roofline, and configs[3] through the Monte-Carlo path: a fixed total of
+frames of the (3,6)-1008 code sharded over the ranks by global frame index, the counter blocks
+all-reduced by the library's NCCL communicator inside the timed region ("experiment_scaling").
+
+One JSON line on stdout (rank 0).  Keys follow the driver's contract.  `value` is wall-clock
+throughput of the whole job: barrier, K launches, the counter all-reduce, barrier (max over
+ranks); kernel_* are CUDA-event times of the launches alone.  The roofline of BP is
+shared-memory bandwidth, that of QP-ADMM the FP64 pipe (messages never leave the SM, so HBM
+traffic is ~0.1 % of peak -- reported under roofline.hbm for completeness).
 """
 import argparse
 import gc
@@ -31,7 +39,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "acg-alp-ldpc_b200"))
-from tests.helpers import load_rows  # noqa: E402  (only the .rows parser)
+from ldpc_b200 import load_rows  # noqa: E402
 
 SEED = 239239239
 BP_SNR, BP_ITERS = -5.0, 100
@@ -213,7 +221,8 @@ def run_reference(args):
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f80", "data": "synthetic",
-        "config": {"workload": "BP(100 iters) on H05 160x280, AWGN @ %g dB" % BP_SNR, "frames_per_step": per_proc * cores},
+        "config": {"workload": WORKLOAD, "frames_per_step": per_proc * cores,
+                   "note": "the reference cannot switch its syndrome exit off; at -5 dB >= 99.8 % of its frames run all 100 iterations"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -221,6 +230,9 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------- GPU arm
+
+WORKLOAD = "BP(100 fixed iters, syndrome exit off) on H05 160x280, AWGN @ %g dB" % BP_SNR
+
 
 def run_gpu(args):
     import torch
@@ -234,9 +246,15 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # the path's only collective is done by the LIBRARY's communicator (ldpc_allreduce_counters, NCCL over NVLink);
+        # torch.distributed is plumbing: it hands the communicator id to the ranks and provides the barrier
+        cid = torch.from_numpy(L.Comm.make_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(cid, 0)
+        comm = L.Comm(rank, world, cid.cpu().numpy(), local)
 
     def barrier():
         if world > 1:
@@ -249,17 +267,21 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allreduce(counters):
+        return comm.allreduce(counters) if comm else counters
+
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     hbm_peak, peak_kind, _ = peaks()
     fp64_peak = L.measure_fp64_peak(local)            # G fp64 FMA instr/s, measured on this GPU
     smem_peak = L.measure_smem_peak(local)            # GB/s of conflict-free shared-memory loads, measured
 
-    def bench_algo(algo, code_name, frames, steps, warmup):
+    def bench_algo(algo, code_name, frames, steps, warmup, snr=None, n_iter=None, e2e=True):
         H = load_rows(code_name)
         m, n = H.shape
         code = L.Code(H=H, device=local)
-        snr = BP_SNR if algo == "bp" else ADMM_SNR
+        snr = (BP_SNR if algo == "bp" else ADMM_SNR) if snr is None else snr
+        n_iter = (BP_ITERS if algo == "bp" else ADMM_ITERS) if n_iter is None else n_iter
         # inputs resident in HBM: two alternating batches, each larger than L2 (126 MB) for BP
         ys = []
         for b in range(2):
@@ -270,20 +292,18 @@ def run_gpu(args):
         bits = torch.empty((frames, n), dtype=torch.uint8, device=dev)
         ok = torch.empty(frames, dtype=torch.uint8, device=dev)
         iters = torch.empty(frames, dtype=torch.int32, device=dev)
-        counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
         def step_device(i):
             y = ys[i & 1]
             if algo == "bp":
-                code.bp_decode_device(y.data_ptr(), frames, snr, BP_ITERS, False, bits.data_ptr(), ok.data_ptr(),
+                code.bp_decode_device(y.data_ptr(), frames, snr, n_iter, False, bits.data_ptr(), ok.data_ptr(),
                                       iters.data_ptr(), 0, sptr)
             else:
-                code.qpadmm_decode_device(y.data_ptr(), frames, snr, ADMM_ALPHA, ADMM_MU, ADMM_ITERS, 0.0,
+                code.qpadmm_decode_device(y.data_ptr(), frames, snr, ADMM_ALPHA, ADMM_MU, n_iter, 0.0,
                                           bits.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, sptr)
 
-        # the clock sampler (an nvidia-smi child) starts BEFORE the warm-up: its start-up (NVML initialisation over all GPUs of
-        # the box) must not fall into the timed region -- one run of six on fresh boxes timed BP at 69 ms per step instead of
-        # 45.6 ms with the sampler starting right at the first timed launch
+        # the clock sampler starts BEFORE the warm-up: its start-up (NVML initialisation over all GPUs of the box) must
+        # not fall into the timed region
         sampler = ClockSampler(local) if rank == 0 else None
         for i in range(warmup):
             step_device(i)
@@ -306,55 +326,56 @@ def run_gpu(args):
         for i in range(steps):
             step_device(i)
         e1.record(stream)
-        # the path's only collective: error/iteration counters, once at the end
-        counts[0] = ok.sum()
-        counts[1] = iters.sum()
-        if world > 1:
-            dist.all_reduce(counts)
+        # the path's only collective, inside the timed region: decoder-flag and iteration counters of the last step,
+        # summed over the ranks by the library's NCCL communicator
+        counts = allreduce({"ok": int(ok.sum().item()), "iters": int(iters.sum().item())})
         barrier()
         t_host1 = time.perf_counter()
         gc.enable()
         clocks = sampler.stop(t_host0, t_host1) if sampler else None
         dev_ms = max_over_ranks(e0.elapsed_time(e1))
         wall_ms = max_over_ranks(1e3 * (t_host1 - t_host0))
-        assert int(iters.min().item()) == (BP_ITERS if algo == "bp" else ADMM_ITERS), "fixed-iteration mode broken"
-
-        # end to end through the public host-buffer API: pinned y in, bits/ok/iters out, every step
-        e2e_frames = frames
-        y_pin = torch.empty((e2e_frames, n), dtype=torch.float64).pin_memory()
-        y_pin.copy_(ys[0].cpu())
-        b_pin = torch.empty((e2e_frames, n), dtype=torch.uint8).pin_memory()
-        ok_pin = torch.empty(e2e_frames, dtype=torch.uint8).pin_memory()
-        it_pin = torch.empty(e2e_frames, dtype=torch.int32).pin_memory()
-        lib = L.lib()
-
-        def step_e2e():
-            if algo == "bp":
-                st = lib.ldpc_bp_decode(code._h, y_pin.data_ptr(), e2e_frames, snr, BP_ITERS, 0, b_pin.data_ptr(),
-                                        ok_pin.data_ptr(), it_pin.data_ptr(), None)
-            else:
-                st = lib.ldpc_qpadmm_decode(code._h, y_pin.data_ptr(), e2e_frames, snr, ADMM_ALPHA, ADMM_MU,
-                                            ADMM_ITERS, 0.0, b_pin.data_ptr(), ok_pin.data_ptr(),
-                                            it_pin.data_ptr(), None)
-            assert st == 0, lib.ldpc_last_error()
-
-        e2e_steps = max(1, min(steps, 3))
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_e2e()
-        barrier()
-        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        assert int(iters.min().item()) == n_iter, "fixed-iteration mode broken"
+        assert counts["iters"] == world * frames * n_iter
 
         info = code.info
+        e2e_res = None
+        if e2e:
+            # end to end through the public host-buffer API: pinned y in, bits/ok/iters out, every step
+            y_pin = torch.empty((frames, n), dtype=torch.float64).pin_memory()
+            y_pin.copy_(ys[0].cpu())
+            b_pin = torch.empty((frames, n), dtype=torch.uint8).pin_memory()
+            ok_pin = torch.empty(frames, dtype=torch.uint8).pin_memory()
+            it_pin = torch.empty(frames, dtype=torch.int32).pin_memory()
+            lib = L.lib()
+
+            def step_e2e():
+                if algo == "bp":
+                    st = lib.ldpc_bp_decode(code._h, y_pin.data_ptr(), frames, snr, n_iter, 0, b_pin.data_ptr(),
+                                            ok_pin.data_ptr(), it_pin.data_ptr(), None)
+                else:
+                    st = lib.ldpc_qpadmm_decode(code._h, y_pin.data_ptr(), frames, snr, ADMM_ALPHA, ADMM_MU, n_iter, 0.0,
+                                                b_pin.data_ptr(), ok_pin.data_ptr(), it_pin.data_ptr(), None)
+                assert st == 0, lib.ldpc_last_error()
+
+            e2e_steps = max(1, min(steps, 3))
+            step_e2e()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_e2e()
+            barrier()
+            e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+            e2e_res = {"value": world * frames * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
+                       "h2d_bytes_per_step": frames * n * 8, "d2h_bytes_per_step": frames * (n + 5)}
+            del y_pin, b_pin, ok_pin, it_pin
+
         units = info["edges"] if algo == "bp" else info["admm_blocks"]
         per_unit = BP_FP64_PER_EDGE_ITER if algo == "bp" else ADMM_FP64_PER_BLOCK_ITER
-        n_iter = BP_ITERS if algo == "bp" else ADMM_ITERS
-        fps_gpu = frames * steps / (dev_ms * 1e-3)                      # this rank's kernel throughput
-        value = world * frames * steps / (dev_ms * 1e-3)
+        fps_gpu = frames * steps / (dev_ms * 1e-3)                      # this rank's kernel throughput (CUDA events)
+        value = world * frames * steps / (wall_ms * 1e-3)               # whole job, wall clock around steps + all-reduce
         achieved = fps_gpu * n_iter * units * per_unit / 1e9            # G fp64 instr/s on one GPU
-        bytes_per_frame = n * 8 + n + 1 + 4
+        bytes_per_frame = n * 8 + n + 1 + 4                             # y in, bits + flag + iteration count out
         k = info["n"] - info["m"]
         fp64 = {"achieved": achieved, "peak": fp64_peak, "unit": "Gop/s (fp64 instr)", "frac": achieved / fp64_peak,
                 "peak_source": "ldpc_measure_fp64_peak on this GPU (8 independent DFMA chains/thread)",
@@ -362,45 +383,134 @@ def run_gpu(args):
                     frames, n_iter, units, "edges" if algo == "bp" else "blocks", per_unit)}
         hbm = {"achieved": fps_gpu * bytes_per_frame / 1e9, "peak": hbm_peak, "unit": "GB/s",
                "frac": fps_gpu * bytes_per_frame / 1e9 / hbm_peak, "peak_kind": peak_kind}
+        # DRAM bytes the launch must move (the ncu captures under profiles/ show dram__bytes within 2 % of it: y is read
+        # once, the outputs are written once, every message stays on chip)
+        traffic = frames * bytes_per_frame
         if algo == "bp":
             # messages never leave the SM: the bounding resource of the likelihood-ratio kernel is shared-memory
             # bandwidth (algorithmic bytes below), then the FP64 pipe; HBM carries 2.5 KB per frame
             smem_bytes = info["edges"] * BP_SMEM_BYTES_PER_EDGE_ITER + info["n"] * BP_SMEM_BYTES_PER_VAR_ITER
             got = fps_gpu * n_iter * smem_bytes / 1e9
             roof = {"bound": "smem", "achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
-                    "traffic": NCU_DRAM_BYTES_PER_FRAME["bp"] * frames * n / 280.0, "bytes_per_frame_iter": smem_bytes,
+                    "traffic": traffic, "bytes_per_frame_iter": smem_bytes,
                     "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)",
                     "work_per_launch": "%d frames x %d iters x %.0f B of shared-memory traffic" % (frames, n_iter, smem_bytes),
                     "fp64": fp64, "hbm": hbm}
         else:
-            roof = dict(fp64, bound="fp64", traffic=NCU_DRAM_BYTES_PER_FRAME["qpadmm"] * frames * n / 280.0, hbm=hbm)
-        res = {
-            "value": value, "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
-            "info_gbit_per_s": value * k / 1e9,
-            "roofline": roof,
-            "e2e": {"value": world * e2e_frames * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": e2e_frames * n * 8, "d2h_bytes_per_step": e2e_frames * (n + 5)},
-            "clocks": clocks, "frames_per_step": frames, "mean_ok": float(counts[0].item()) / (world * frames),
-            "kernel": kernel,
-        }
-        if algo == "qpadmm":
+            roof = dict(fp64, bound="fp64", traffic=traffic, hbm=hbm)
             # shared-memory traffic of the check-centric kernel per frame-iteration: the row terms w are written once
             # per block (32 B) and gathered once per (original variable, check) incidence (32 B); v is written once
             # per original variable and gathered once per incidence (8 B); q + alpha/2 and inv_coef are read per variable
             inc = info["edges"]
             smem_bytes = info["admm_blocks"] * 32 + inc * 32 + inc * 8 + info["n"] * 24
             got = fps_gpu * n_iter * smem_bytes / 1e9
-            res["roofline"]["smem"] = {"achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
-                                       "bytes_per_frame_iter": smem_bytes,
-                                       "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)"}
+            roof["smem"] = {"achieved": got, "peak": smem_peak, "unit": "GB/s", "frac": got / smem_peak,
+                            "bytes_per_frame_iter": smem_bytes,
+                            "peak_source": "ldpc_measure_smem_peak on this GPU (conflict-free LDS.128)"}
+        res = {
+            "value": value, "ms_per_step": wall_ms / steps, "kernel_ms_per_step": dev_ms / steps,
+            "wall_ms_per_step": wall_ms / steps, "kernel_value": world * fps_gpu,
+            "info_gbit_per_s": value * k / 1e9, "roofline": roof, "clocks": clocks, "frames_per_step": frames,
+            "iters": n_iter, "snr_db": snr, "mean_ok": counts["ok"] / (world * frames), "kernel": kernel,
+        }
+        if e2e_res:
+            res["e2e"] = e2e_res
         code.close()
+        del ys, bits, ok, iters
+        torch.cuda.empty_cache()
         return res
 
+    def as_run(algo, code_name, snr, frames, max_iter):
+        """experiment mode (device-side codewords, AWGN, decoding with the reference's stopping rules, verdict,
+        counters): frames/s as the decoders really run, with the mean iterations per frame"""
+        H = load_rows(code_name)
+        code = L.Code(H=H, device=local)
+        dec = L.BeliefPropagationDecoder(max_iter) if algo == "bp" else L.QPADMMDecoder(ADMM_ALPHA, ADMM_MU, max_iter, 1e-5)
+        begin = rank * frames
+        code.experiment(dec, snr, SEED, begin, min(frames, 4096))            # warm-up (tables, schedules)
+        barrier()
+        t0 = time.perf_counter()
+        r = code.experiment(dec, snr, SEED, begin, frames)
+        tot = allreduce({k: r[k] for k in L.CNT_NAMES})
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        code.close()
+        return {"workload": "%s on %s @ %g dB, early exit as the reference" % (dec.name(), code_name, snr),
+                "frames": world * frames, "value": world * frames / wall, "unit": "frames/s",
+                "kernel_seconds": max_over_ranks(r["gpu_seconds"]), "mean_iters": tot["sum_iters"] / tot["total"],
+                "fer": 1.0 - tot["correct"] / tot["total"]}
+
+    def channel_roofline(code_name, frames):
+        """device Philox4x32-10 + Box-Muller channel (utils/channel.h:19-26): y written to HBM, 8 n bytes per frame"""
+        H = load_rows(code_name)
+        n = H.shape[1]
+        code = L.Code(H=H, device=local)
+        y = torch.empty((frames, n), dtype=torch.float64, device=dev)
+        code.channel_device(SEED, 0, frames, -3.0, y.data_ptr(), 0, sptr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(3):
+            code.channel_device(SEED, (i + 1) * frames, frames, -3.0, y.data_ptr(), 0, sptr)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        code.close()
+        gbs = frames * n * 8 / (ms * 1e-3) / 1e9
+        return {"workload": "channel_kernel: %d frames x %d samples (Philox4x32-10 + fp64 Box-Muller), y to HBM" % (frames, n),
+                "frames_per_s": frames / (ms * 1e-3), "samples_per_s": frames * n / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "peak_kind": peak_kind, "traffic": frames * n * 8}}
+
+    def experiment_scaling(total_bp, total_admm):
+        """BASELINE.json configs[3]: the (3,6)-1008 code, a FIXED total of frames sharded over the ranks by global frame
+        index through ldpc_experiment_run, counter blocks all-reduced by NCCL inside the timed wall.  The counters are
+        functions of the global frame range only: identical for 1/2/4/8 GPUs (compare `counters` across the SCALE lines);
+        each run also checks the invariance itself on a small range (sharded + all-reduced == one rank alone)."""
+        import sharding
+        H = load_rows("reg_3_6_1008")
+        code = L.Code(H=H, device=local)
+        out = {}
+        for name, dec, snr, total in (("bp", L.BeliefPropagationDecoder(100), -2.0, total_bp),
+                                      ("qpadmm", L.QPADMMDecoder(ADMM_ALPHA, ADMM_MU, 1000, 1e-5), -1.0, total_admm)):
+            small = 1536
+            b, e = sharding.shard_range(small, rank, world)
+            part = code.experiment(dec, snr, SEED, 10 ** 9 + b, e - b)
+            summed = allreduce({k: part[k] for k in L.CNT_NAMES})
+            alone = code.experiment(dec, snr, SEED, 10 ** 9, small)
+            assert all(summed[k] == alone[k] for k in L.CNT_NAMES), "sharded counters differ from a single rank's"
+            b, e = sharding.shard_range(total, rank, world)
+            barrier()
+            t0 = time.perf_counter()
+            r = code.experiment(dec, snr, SEED, b, e - b)
+            tot = allreduce({k: r[k] for k in L.CNT_NAMES})
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            out[name] = {"workload": "%s on reg_3_6_1008 @ %g dB, %d frames in total (strong scaling), sharded by global frame "
+                                     "index, NCCL all-reduce of the counter block inside the timed region" % (dec.name(), snr, total),
+                         "value": total / wall, "unit": "frames/s", "wall_s": wall, "scaling": "strong",
+                         "kernel_seconds_max": max_over_ranks(r["gpu_seconds"]), "counters": tot,
+                         "mean_iters": tot["sum_iters"] / tot["total"], "invariance_checked_on_frames": small}
+        code.close()
+        return out
+
     bp = bench_algo("bp", "H05", args.frames, args.steps, args.warmup)
-    admm = bench_algo("qpadmm", "optimalH", max(1024, args.frames // 8), args.steps, args.warmup)
-    # the other code north_star names: synthetic (3,6)-regular n = 1008 (BASELINE.json configs[3]), same settings
-    big_bp = bench_algo("bp", "reg_3_6_1008", max(1024, args.frames // 4), args.steps, args.warmup)
-    big_admm = bench_algo("qpadmm", "reg_3_6_1008", max(512, args.frames // 32), args.steps, args.warmup)
+    extra = {}
+    if not args.headline_only:
+        extra["bp_optimalH"] = bench_algo("bp", "optimalH", args.frames, args.steps, args.warmup, e2e=False)
+        admm = bench_algo("qpadmm", "optimalH", max(1024, args.frames // 8), args.steps, args.warmup)
+        # main.cpp:31 runs QP-ADMM with max_iter = 10000: the same kernel, ten times the iterations per frame
+        extra["qpadmm_10000"] = bench_algo("qpadmm", "optimalH", max(1024, args.frames // 64), max(1, args.steps // 2), 1,
+                                           n_iter=10000, e2e=False)
+        # the other code north_star names: synthetic (3,6)-regular n = 1008 (BASELINE.json configs[3]), same settings
+        big_bp = bench_algo("bp", "reg_3_6_1008", max(1024, args.frames // 4), args.steps, args.warmup)
+        big_admm = bench_algo("qpadmm", "reg_3_6_1008", max(512, args.frames // 32), args.steps, args.warmup)
+        as_run_pts = [as_run("bp", "H05", -3.0, args.frames, 100), as_run("bp", "H05", 0.0, 4 * args.frames, 100),
+                      as_run("qpadmm", "optimalH", -3.0, max(1024, args.frames // 8), 10000),
+                      as_run("qpadmm", "optimalH", 0.0, args.frames, 10000)]
+        chan = channel_roofline("H05", args.frames) if rank == 0 else None
+        barrier()
+        exp_scale = experiment_scaling(args.exp_frames, max(2048, args.exp_frames // 16))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -413,34 +523,47 @@ def run_gpu(args):
                    "sample": "%d procs x %d frames, unmodified reference BP(100) on H05 @ %g dB, 1 thread/process, "
                              "%.1f s wall" % (cores, per_proc, BP_SNR, wall)}
     if rank == 0:
+        pick = ("value", "ms_per_step", "kernel_ms_per_step", "kernel_value", "info_gbit_per_s", "roofline", "clocks",
+                "kernel", "frames_per_step", "iters", "snr_db")
         line = {
             "metric": "decoded frames/sec (BP, fixed 100 iters)", "value": bp["value"], "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": bp["ms_per_step"],
+            "kernel_ms_per_step": bp["kernel_ms_per_step"], "wall_ms_per_step": bp["wall_ms_per_step"],
+            "kernel_value": bp["kernel_value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BP(100 fixed iters, syndrome exit off) on H05 160x280, AWGN @ %g dB, "
-                                   "%d frames/step/GPU (configs[1]: 1e7 frames/point = %d steps)" % (
-                                       BP_SNR, args.frames, -(-10 ** 7 // args.frames)),
-                       "frames_per_step_per_gpu": args.frames, "parallelism": "frames sharded over %d GPU(s)" % world,
-                       "l2_policy": "inputs larger than L2: two alternating %d MB batches" % (
-                           args.frames * 280 * 8 >> 20)},
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.frames,
+                       "steps_for_1e7_frames_per_point": -(-10 ** 7 // args.frames),
+                       "parallelism": "frames sharded over %d GPU(s)" % world,
+                       "timed_region": "barrier, K decode launches, NCCL all-reduce of the counters (ldpc_allreduce_counters), "
+                                       "barrier; wall clock, max over ranks (kernel_* = CUDA events around the launches alone)",
+                       "l2_policy": "inputs larger than L2: two alternating %d MB batches" % (args.frames * 280 * 8 >> 20)},
             "info_gbit_per_s": bp["info_gbit_per_s"], "roofline": bp["roofline"], "e2e": bp["e2e"],
             "clocks": bp["clocks"], "gpu_launches": args.steps, "kernel": bp["kernel"], "cpu_baseline": cpu,
-            "qpadmm": {"metric": "decoded frames/sec (QP-ADMM, fixed 1000 iters, eps_stop=0)",
-                       "config": {"workload": "QP-ADMM(alpha=%g, mu=%g, 1000 iters) on optimalH 160x280 @ %g dB" % (
-                           ADMM_ALPHA, ADMM_MU, ADMM_SNR), "frames_per_step_per_gpu": admm["frames_per_step"]},
-                       "value": admm["value"], "ms_per_step": admm["ms_per_step"],
-                       "info_gbit_per_s": admm["info_gbit_per_s"], "roofline": admm["roofline"], "e2e": admm["e2e"],
-                       "clocks": admm["clocks"], "kernel": admm["kernel"]},
-            "reg_3_6_1008": {
+        }
+        if not args.headline_only:
+            line["bp_optimalH"] = dict({k: extra["bp_optimalH"][k] for k in pick},
+                                       workload="BP(100 fixed iters) on optimalH 160x280 @ %g dB" % BP_SNR)
+            line["qpadmm"] = dict({k: admm[k] for k in pick + ("e2e",)},
+                                  metric="decoded frames/sec (QP-ADMM, fixed 1000 iters, eps_stop=0)",
+                                  config={"workload": "QP-ADMM(alpha=%g, mu=%g, 1000 iters) on optimalH 160x280 @ %g dB" % (
+                                      ADMM_ALPHA, ADMM_MU, ADMM_SNR), "frames_per_step_per_gpu": admm["frames_per_step"]})
+            line["qpadmm_10000"] = dict({k: extra["qpadmm_10000"][k] for k in pick},
+                                        workload="QP-ADMM(alpha=%g, mu=%g, 10000 fixed iters, main.cpp:31) on optimalH @ %g dB" % (
+                                            ADMM_ALPHA, ADMM_MU, ADMM_SNR))
+            line["reg_3_6_1008"] = {
                 "config": {"workload": "synthetic (3,6)-regular 504x1008 (configs[3]): BP(100 fixed iters) @ %g dB, %d frames/step/GPU; "
                                        "QP-ADMM(alpha=%g, mu=%g, 1000 fixed iters) @ %g dB, %d frames/step/GPU" % (
                                            BP_SNR, big_bp["frames_per_step"], ADMM_ALPHA, ADMM_MU, ADMM_SNR,
                                            big_admm["frames_per_step"])},
-                "bp": {k: big_bp[k] for k in ("value", "ms_per_step", "info_gbit_per_s", "roofline", "e2e", "clocks", "kernel")},
-                "qpadmm": {k: big_admm[k] for k in ("value", "ms_per_step", "info_gbit_per_s", "roofline", "e2e", "clocks", "kernel")},
-            },
-        }
+                "bp": {k: big_bp[k] for k in pick + ("e2e",)},
+                "qpadmm": {k: big_admm[k] for k in pick + ("e2e",)},
+            }
+            line["as_run"] = as_run_pts
+            line["channel"] = chan
+            line["experiment_scaling"] = exp_scale
         emit(line)
+    if comm:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -479,6 +602,9 @@ def main():
                          "30-50 ms stalls these boxes show now and then (one run in five, whatever samples the clocks) "
                          "stay below a few per cent of the timed region")
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per core of one reference sample")
+    ap.add_argument("--exp-frames", type=int, default=1 << 21,
+                    help="total BP frames of the experiment-mode scaling arm on the (3,6)-1008 code (QP-ADMM: 1/16)")
+    ap.add_argument("--headline-only", action="store_true", help="only the headline workload (BP on H05)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -178,6 +178,30 @@ int ldpc_qpadmm_grid_run(const ldpc_code_t *code, int32_t points, const double *
                          uint64_t frame_count, int32_t codeword_source, const uint8_t *words, uint64_t n_words,
                          uint64_t *counters, double *gpu_seconds);
 
+/* ---- multi-GPU: frames are sharded by GLOBAL frame index, so the counters are identical for any
+ * number of GPUs, and the path's only collective is one all-reduce (sum, uint64) of the counter block over NVLink,
+ * done by NCCL (libnccl.so.2, loaded at first use; LDPC_E_UNSUPPORTED when it cannot be loaded).
+ * It replaces merge_exp_results() after pthread_join (experiment.h:70-78, 125-139).
+ *
+ * One process, several GPUs (the C++ drivers): codes[g] is the handle of the same H on device g.  The shards
+ * [frame_begin + frame_count * g / n, frame_begin + frame_count * (g + 1) / n) run concurrently, the counter blocks are
+ * all-reduced on the devices (ncclCommInitAll communicator, cached per device list) and the sum is returned.
+ * gpu_seconds (may be NULL) = the longest device time of a shard. */
+int ldpc_experiment_run_multi(const ldpc_code_t *const *codes, int32_t n_devices, const ldpc_algo_cfg_t *cfg, double snr,
+                              uint64_t seed, uint64_t frame_begin, uint64_t frame_count, int32_t codeword_source,
+                              const uint8_t *words, uint64_t n_words, uint64_t counters[LDPC_CNT_COUNT],
+                              double *gpu_seconds);
+
+/* One process per GPU (torchrun / MPI style): rank 0 makes an id (128 bytes) and hands it to the other ranks by any
+ * means (bench.py: torch.distributed broadcast of the bytes); every rank joins with ldpc_comm_init on its device, then
+ * ldpc_allreduce_counters sums `count` 64-bit counters in place (host array) over all ranks. */
+#define LDPC_COMM_ID_BYTES 128
+typedef struct ldpc_comm ldpc_comm_t;
+int ldpc_comm_unique_id(uint8_t id[LDPC_COMM_ID_BYTES]);
+int ldpc_comm_init(int32_t rank, int32_t world, const uint8_t id[LDPC_COMM_ID_BYTES], int device, ldpc_comm_t **out);
+int ldpc_allreduce_counters(ldpc_comm_t *comm, uint64_t *counters, int32_t count);
+void ldpc_comm_destroy(ldpc_comm_t *comm);
+
 /* ---- pinned host buffers for the host-pointer entry points (optional: any
  * host memory works, pinned memory makes the copies asynchronous). */
 int ldpc_host_alloc(void **ptr, uint64_t bytes);

@@ -13,16 +13,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 
-def load_rows(name):
-    """Dense uint8 matrix from acg-alp-ldpc_b200/data/<name>.rows."""
-    lines = [l for l in open(os.path.join(DATA, name + ".rows")) if not l.startswith("#")]
-    m, n = (int(x) for x in lines[0].split())
-    H = np.zeros((m, n), np.uint8)
-    for r, line in enumerate(lines[1:1 + m]):
-        vals = [int(x) for x in line.split()]
-        assert vals[0] == len(vals) - 1
-        H[r, vals[1:]] = 1
-    return H
+from ldpc_b200 import load_rows  # noqa: E402,F401  (the .rows parser lives in the package)
 
 
 def small_irregular_code(seed=7, m=12, n=24):

@@ -530,3 +530,33 @@ def test_qpadmm_grid_on_a_code_with_few_checks(gpu_lib, oracle):
         want = oracle.experiment("qpadmm", csr, m, n, snr, iters, SEED, 0, frames, alpha=a, mu=mu_, eps_stop=eps)
         assert all(got[k] == want[k] for k in want), (a, mu_, got, want)
     code.close()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_entry_points(gpu_lib, codes, oracle):
+    """ldpc_experiment_run_multi / ldpc_comm_* / ldpc_allreduce_counters.  The driver's GPU tests see one
+    device, so this covers the single-device case of both (a world of one rank) and -- when more devices are visible --
+    the sharded run: identical counters for any device count."""
+    L = gpu_lib
+    H, code, csr = codes["optimalH"]
+    m, n = H.shape
+    dec = L.QPADMMDecoder(1.2, 0.55, 300, 1e-5)
+    want = oracle.experiment("qpadmm", csr, m, n, -2.0, 300, SEED, 40, 90, alpha=1.2, mu=0.55, eps_stop=1e-5)
+    got = L.experiment_multi([code], dec, -2.0, SEED, 40, 90)
+    assert all(got[k] == want[k] for k in want)
+    ndev = L.device_count()
+    if ndev > 1:
+        handles = [code] + [L.Code(H=H, device=g) for g in range(1, ndev)]
+        for cnt in (2, ndev):
+            got = L.experiment_multi(handles[:cnt], dec, -2.0, SEED, 40, 90)
+            assert all(got[k] == want[k] for k in want), cnt
+        bp = L.BeliefPropagationDecoder(100)
+        one = code.experiment(bp, -3.0, SEED, 0, 5000)
+        many = L.experiment_multi(handles, bp, -3.0, SEED, 0, 5000)
+        assert all(one[k] == many[k] for k in want)
+    # a communicator of one rank: the all-reduce is the identity
+    comm = L.Comm(0, 1, L.Comm.make_id(), 0)
+    assert comm.allreduce(want) == want
+    vec = comm.allreduce(np.arange(37, dtype=np.uint64) << np.uint64(40))
+    assert (vec == np.arange(37, dtype=np.uint64) << np.uint64(40)).all()
+    comm.close()
