@@ -57,15 +57,23 @@ public:
 
     CodeRef get(const TMatrix &H, int device = 0) {
         CsrMatrix key = to_csr(H);
+        {
+            lock_guard<mutex> lock(mu_);
+            auto it = codes_.find(make_pair(device, key));
+            if (it != codes_.end()) return it->second;
+        }
+        // compile and upload OUTSIDE the lock: optimize_H.cpp evaluates several proposals (several new H) at once, one
+        // host thread and one GPU each, and a compile takes milliseconds
+        vector<int32_t> cols = key.col_idx;
+        if (cols.empty()) cols.push_back(0);
+        ldpc_code_t *raw = nullptr;
+        if (ldpc_code_create(key.m, key.n, key.row_ptr.data(), cols.data(), device, &raw) != LDPC_OK)
+            die("ldpc_code_create");
+        CodeRef fresh(raw, [](ldpc_code_t *c) { ldpc_code_destroy(c); });
         lock_guard<mutex> lock(mu_);
         CodeRef &slot = codes_[make_pair(device, key)];
-        if (!slot) {
-            vector<int32_t> cols = key.col_idx;
-            if (cols.empty()) cols.push_back(0);
-            ldpc_code_t *raw = nullptr;
-            if (ldpc_code_create(key.m, key.n, key.row_ptr.data(), cols.data(), device, &raw) != LDPC_OK)
-                die("ldpc_code_create");
-            slot = CodeRef(raw, [](ldpc_code_t *c) { ldpc_code_destroy(c); });
+        if (!slot) {                                      // (else another thread was faster: ours is dropped)
+            slot = fresh;
             if (codes_.size() > 64) evict(device, key);   // optimize_H.cpp proposes a new H every step
         }
         return slot;

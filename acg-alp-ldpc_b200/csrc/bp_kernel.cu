@@ -311,7 +311,7 @@ static int launch_bp_f(BpParams &p, const ldpc_code *c, int threads, int64_t fra
     p.jobs_v = s.jobs_v; p.jobs_c = s.jobs_c; p.rounds_v = s.rounds_v; p.rounds_c = s.rounds_c;
     const size_t smem = bp_smem_bytes(c, F);
     auto kernel = bp_kernel<F, MAXT, MINB>;
-    LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    LDPC_CUDA(allow_max_dynamic_smem(kernel));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));

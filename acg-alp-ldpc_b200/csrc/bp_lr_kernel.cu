@@ -989,7 +989,7 @@ int launch_bp_lr(const ldpc_code *c, const FrameIO &fio, int64_t frames, double 
     const int threads = teams * gt;
     const size_t smem = tables + (size_t) teams * team_bytes;
     LrKernel kernel = lr_kernel(F, threads, soft, wide);
-    LDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    LDPC_CUDA(allow_max_dynamic_smem(kernel));
     int per_sm = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) return fail(LDPC_E_UNSUPPORTED, "BP state of this code does not fit on one SM");

@@ -178,6 +178,18 @@ int measure_smem_peak(int device, double *gbytes_per_s);
 int debug_bpmath(int device, int count, const double *a, const double *ev, const double *od, double *out_exp,
                  double *out_log);
 
+// Opts a kernel into the full dynamic shared memory of an SM (227 KB minus its static share).  The attribute is
+// per-function state shared by every host thread: setting it to the size of ONE launch races with a concurrent launch
+// of another code that needs more (optimize_H.cpp evaluates several H at once) -- "invalid argument" at launch; the
+// constant maximum cannot race.
+template <typename Kernel>
+inline cudaError_t allow_max_dynamic_smem(Kernel kernel) {
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int) attr.sharedSizeBytes);
+}
+
 // sigma^2 exactly as utils/channel.h:12 computes it on the host
 double llr_variance(double snr);
 

@@ -961,7 +961,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     p.stream_rows = t->stream_rows;
     p.slot_e = t->var_e;
     ChkKernel fn = chk_kernel_for(F, t->max_nb, grid, two);
-    LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    LDPC_CUDA(allow_max_dynamic_smem(fn));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     LDPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));

@@ -307,7 +307,7 @@ static int choose_shape(const ldpc_code *c, int64_t frames, AdmmShape *out, int 
             const AdmmShape s = admm_shape(c, F, kb);
             if (s.threads > 512 || s.smem > 227 * 1024) continue;
             AdmmKernel fn = kernel_for(F, kb);
-            LDPC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem));
+            LDPC_CUDA(allow_max_dynamic_smem(fn));
             int per_sm = 0;
             LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s.threads, s.smem));
             if (per_sm < 1) continue;

@@ -6,7 +6,7 @@
 // written to the save path.  Every proposal is a new H, hence a new code handle.
 //
 // Environment: LDPC_OPT_ITERS (default 10000), LDPC_OPT_SAVE (default data/optimalH.txt), LDPC_OPT_WINDOW (proposals
-//              evaluated speculatively at once, default = the number of GPUs; the trajectory does not depend on it),
+//              evaluated speculatively at once, default = twice the number of GPUs; the trajectory does not depend on it),
 //              LDPC_OPT_START (a matrix stem to start from instead of a random one).
 #include <memory>
 #include <mutex>
@@ -202,7 +202,9 @@ int main() {
                                                      : random_permutation_matrix(20, 8, 14);
     mt19937 rnd(239);
     // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value)
-    const int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : ldpc_host::visible_gpus();
+    // default: two proposals in flight per GPU, so that the host work of one (GetOrtogonal, 1000 codewords, compiling
+    // and uploading the new H) overlaps the evaluation of the other
+    const int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : 2 * ldpc_host::visible_gpus();
     TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
 
     cout << FER(H, 10000) << endl;

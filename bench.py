@@ -307,6 +307,8 @@ def run_gpu(args):
         sampler = ClockSampler(local) if rank == 0 else None
         for i in range(warmup):
             step_device(i)
+        int(ok.sum().item()) + int(iters.sum().item())       # the reductions of the timed region are loaded and warm too
+        allreduce({"ok": 0, "iters": 0})
         torch.cuda.synchronize()
         if sampler:
             sampler.wait_ready()
@@ -326,11 +328,18 @@ def run_gpu(args):
         for i in range(steps):
             step_device(i)
         e1.record(stream)
+        t_a = time.perf_counter()
         # the path's only collective, inside the timed region: decoder-flag and iteration counters of the last step,
         # summed over the ranks by the library's NCCL communicator
-        counts = allreduce({"ok": int(ok.sum().item()), "iters": int(iters.sum().item())})
+        mine = {"ok": int(ok.sum().item()), "iters": int(iters.sum().item())}
+        t_b = time.perf_counter()
+        counts = allreduce(mine)
+        t_c = time.perf_counter()
         barrier()
         t_host1 = time.perf_counter()
+        if os.environ.get("BENCH_TRACE"):
+            sys.stderr.write("trace %s %s: launches %.1f ms, kernels+sums %.1f ms, all-reduce %.1f ms, barrier %.1f ms\n" % (
+                algo, code_name, 1e3 * (t_a - t_host0), 1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_host1 - t_c)))
         gc.enable()
         clocks = sampler.stop(t_host0, t_host1) if sampler else None
         dev_ms = max_over_ranks(e0.elapsed_time(e1))
