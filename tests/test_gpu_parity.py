@@ -560,3 +560,45 @@ def test_multi_gpu_entry_points(gpu_lib, codes, oracle):
     vec = comm.allreduce(np.arange(37, dtype=np.uint64) << np.uint64(40))
     assert (vec == np.arange(37, dtype=np.uint64) << np.uint64(40)).all()
     comm.close()
+
+
+@pytest.mark.gpu
+def test_results_do_not_depend_on_the_schedule(codes, monkeypatch):
+    """Stand-in for compute-sanitizer's racecheck (closed on this pool, profiles/r02_compute_sanitizer_closed.txt):
+    every launch shape -- frames per team / CTA, teams per CTA, soft output on and off -- decodes the same ragged batches
+    several times and must reproduce bits, flags, iteration counts and soft outputs BIT FOR BIT.  The kernels update
+    messages in place, double-buffer their control words by trip parity and refill slots between two barriers: a race
+    there shows up as a run-to-run or shape-to-shape difference."""
+    for name, snr, sizes in (("optimalH", -3.0, (7, 301, 2500)), ("H05", -2.5, (301,)), ("reg_3_6_1008", -1.5, (5, 130))):
+        H, code, _ = codes[name]
+        alpha, mu = ADMM[name]
+        for frames in sizes:
+            y = code.channel(SEED, 77000, frames, snr)
+            base = None
+            for F in ("2", "4", "8"):
+                for teams in ("1", "2", "5"):
+                    monkeypatch.setenv("LDPC_BP_F", F)
+                    monkeypatch.setenv("LDPC_BP_TEAMS", teams)
+                    for rep in range(2):
+                        b, ok, it, post = code.bp_decode(y, snr, 100, soft=(rep == 0))
+                        sig = (b.tobytes(), ok.tobytes(), it.tobytes())
+                        if base is None:
+                            base, base_post = sig, post.copy()
+                        assert sig == base, (name, frames, F, teams, rep)
+                        # the products of a node are taken in layout order, which depends on F: soft outputs agree to rounding
+                        if rep == 0:
+                            conv = ok == 1
+                            assert np.allclose(post[conv], base_post[conv], rtol=1e-9, atol=0), (name, frames, F, teams)
+            monkeypatch.delenv("LDPC_BP_F")
+            monkeypatch.delenv("LDPC_BP_TEAMS")
+            base = None
+            for F in ("1", "2", "4"):
+                if name == "reg_3_6_1008" and F != "1":
+                    continue
+                monkeypatch.setenv("LDPC_ADMM_F", F)
+                for rep in range(2):
+                    b, ok, it, v = code.qpadmm_decode(y[:min(frames, 400)], snr, alpha, mu, 300, 1e-5)
+                    sig = (b.tobytes(), ok.tobytes(), it.tobytes(), v.tobytes())
+                    base = base or sig
+                    assert sig == base, (name, frames, F, rep)
+            monkeypatch.delenv("LDPC_ADMM_F")
