@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     T.sync();
     const uint4 kept = lds_u32x4(smem_addr(msg) + tid * 32), kept2 = lds_u32x4(smem_addr(msg) + tid * 32 + 16);
     T.sync();
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr(msg) + tid * 4), "r"((uint32_t) gt * 4) : "memory");
+    T.sync();
+    const uint32_t row = lds_u32(smem_addr(msg) + tid * 4);      // bytes between the rows of a step table
+    T.sync();
     A.msg = kept.x;
     A.dec = kept.y;
     A.off_lch = p.off_lch;
@@ -279,7 +283,6 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     A.range = (int) kept2.z;
     A.lo = (int) kept2.w;
     const uint32_t a_steps_c = kept.z, a_steps_v = a_steps_c + p.steps_c * gt * 4;
-    const uint32_t row = (uint32_t) gt * 4;
     const unsigned pair_shift = kept.w, pair_bits = 3u << pair_shift;
 
     team_slots_init(T, S);                      // (after the round trip: its scratch may reach into the control block)
