@@ -131,6 +131,7 @@ struct LrAddr {
     uint32_t off_lch, off_post;
     uint32_t rec;               // the record table
     int neg_lo, range, lo;      // clamp constants: -hi word of exp(-C1), hi(exp(C1)) - hi(exp(-C1)), hi word of exp(-C1)
+    int lo_neg;                 // lo with the sign bit set (decision 1)
 };
 
 // ---- variable node of degree D, two frames: VNode::message (bp.h:77-83), estimate (bp.h:85-90), decision (bp.h:193)
@@ -164,12 +165,14 @@ __device__ __forceinline__ void lr_var_update(const LrAddr &A, uint32_t rec, int
     }
     const P2 tot = lam[d - 1] * x[d - 1];       // posterior likelihood ratios
     const bool one_a = tot.a <= 1.0, one_b = tot.b <= 1.0;   // estimate <= 0 -> bit 1 (bp.h:193)
-    const int sa = A.lo + (one_a ? (int) 0x80000000 : 0), sb = A.lo + (one_b ? (int) 0x80000000 : 0);
+    const int sa = one_a ? A.lo_neg : A.lo, sb = one_b ? A.lo_neg : A.lo;     // one select each: both constants live in registers
     const int neg_lo = A.neg_lo, range = A.range;
 #pragma unroll
     for (int j = 0; j < d; ++j)
         st_p2(A.msg + w[1 + j], P2{clamp_sign(lam[j].a, neg_lo, range, sa), clamp_sign(lam[j].b, neg_lo, range, sb)});
-    sts_u16(A.dec + (w[0] >> 3), (uint32_t) ((one_a ? 1 : 0) | (one_b ? 0x100 : 0)));
+    uint32_t bits2 = one_b ? 0x100u : 0u;
+    if (one_a) bits2 += 1u;
+    sts_u16(A.dec + (w[0] >> 3), bits2);
     if (SOFT) st_p2(A.msg + A.off_post + w[0], tot);
 }
 
@@ -270,9 +273,11 @@ __global__ void __launch_bounds__(MAXT, 1) bp_lr_kernel(const BpLrParams p) {
     T.sync();
     const uint4 kept = lds_u32x4(smem_addr(msg) + tid * 32), kept2 = lds_u32x4(smem_addr(msg) + tid * 32 + 16);
     T.sync();
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr(msg) + tid * 4), "r"((uint32_t) gt * 4) : "memory");
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_addr(msg) + tid * 8), "r"((uint32_t) gt * 4),
+                 "r"(p.clamp_lo + (int) 0x80000000) : "memory");
     T.sync();
-    const uint32_t row = lds_u32(smem_addr(msg) + tid * 4);      // bytes between the rows of a step table
+    const uint32_t row = lds_u32(smem_addr(msg) + tid * 8);      // bytes between the rows of a step table
+    A.lo_neg = (int) lds_u32(smem_addr(msg) + tid * 8 + 4);
     T.sync();
     A.msg = kept.x;
     A.dec = kept.y;

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(HERE, "libldpc_b200.so")     # (the override is for A/B timing of two builds)
 
 CNT_NAMES = ["total", "correct", "pseudo", "decoder_fail", "bit_errors", "sum_hamming", "sum_hamming_ok",
              "sum_hamming_wrong", "sum_iters", "frames_with_bits"]

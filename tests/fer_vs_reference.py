@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "acg-alp-ldpc_b200"))
 sys.path.insert(0, ROOT)
-from tests.helpers import load_rows  # noqa: E402
+from ldpc_b200 import load_rows  # noqa: E402
 
 SNRS = [-5.0 + 0.5 * i for i in range(11)]          # main.cpp:27
 DECODERS = [("BP", "bp", dict(max_iter=100)), ("QP-ADMM", "qpadmm", dict(max_iter=10000, alpha=1.2, mu=0.55, eps_stop=1e-5))]

@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "acg-alp-ldpc_b200"))
-from tests.helpers import load_rows  # noqa: E402
+from ldpc_b200 import load_rows  # noqa: E402
 
 SEED = 239239239
 ADMM = {"optimalH": (1.2, 0.55), "H05": (1.95, 0.5), "reg_3_6_1008": (1.2, 0.55)}
@@ -50,9 +50,9 @@ def main():
     args = ap.parse_args()
     import ldpc_b200 as L
     cores = len(os.sched_getaffinity(0))
-    points = [("bp", "optimalH", s, 100, args.frames) for s in (-4.0, -3.0, -2.0, -1.0)] + \
-             [("bp", "H05", s, 100, args.frames) for s in (-3.0, -2.0)] + \
-             [("bp", "reg_3_6_1008", 0.0, 100, args.frames // 8)] + \
+    points = [("bp", "optimalH", s, 100, args.frames) for s in (-4.0, -3.0, -2.0, -1.0, 1.0, 3.0)] + \
+             [("bp", "H05", s, 100, args.frames) for s in (-3.0, -2.0, -0.5, 2.0)] + \
+             [("bp", "reg_3_6_1008", s, 100, args.frames // 8) for s in (-2.0, -1.5, 0.0)] + \
              [("qpadmm", "optimalH", s, 1000, args.frames // 2) for s in (-3.0, -2.0)] + \
              [("qpadmm", "H05", -2.5, 1000, args.frames // 4), ("qpadmm", "reg_3_6_1008", -1.0, 300, args.frames // 20)]
     lines = ["# per-frame parity campaign: CUDA kernels vs CPU oracle on identical channel samples (seed %d)" % SEED,
