@@ -521,6 +521,10 @@ def run_gpu(args):
         barrier()
         exp_scale = experiment_scaling(args.exp_frames, max(2048, args.exp_frames // 16))
 
+    exp_only = None
+    if args.headline_only and args.with_experiment:
+        exp_only = experiment_scaling(args.exp_frames, max(2048, args.exp_frames // 16))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.oracle import have_ref
@@ -570,6 +574,8 @@ def run_gpu(args):
             line["as_run"] = as_run_pts
             line["channel"] = chan
             line["experiment_scaling"] = exp_scale
+        elif exp_only:
+            line["experiment_scaling"] = exp_only
         emit(line)
     if comm:
         comm.close()
@@ -614,6 +620,8 @@ def main():
     ap.add_argument("--exp-frames", type=int, default=1 << 21,
                     help="total BP frames of the experiment-mode scaling arm on the (3,6)-1008 code (QP-ADMM: 1/16)")
     ap.add_argument("--headline-only", action="store_true", help="only the headline workload (BP on H05)")
+    ap.add_argument("--with-experiment", action="store_true",
+                    help="with --headline-only: also the experiment-mode strong-scaling arm (counters comparable across N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
