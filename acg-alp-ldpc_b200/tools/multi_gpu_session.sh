@@ -19,7 +19,8 @@ python bench.py --gpus 1 --steps 5 --warmup 3 --headline-only --with-experiment 
 python acg-alp-ldpc_b200/tools/config3_run.py --frames $FRAMES3 > $OUT/r02_config3_1e9_n$N.txt 2> $OUT/r02_config3_1e9_n$N.err; cat $OUT/r02_config3_1e9_n$N.txt | cut -c1-160
 cd acg-alp-ldpc_b200 && g++ -std=c++17 -pthread -O2 -I. -I../include optimize_H.cpp -o /tmp/optimize_H -L. -lldpc_b200 -Wl,-rpath,$PWD
 for g in 1 $N; do
-  /usr/bin/time -f "optimize_H gpus=$g wall %e s" env LDPC_GPUS=$g LDPC_OPT_ITERS=$OPT_ITERS LDPC_OPT_SAVE=/tmp/opt_g$g.txt LDPC_OPT_START=data/H05 /tmp/optimize_H > ../$OUT/r02_optimize_H_1000_gpus$g.txt 2> ../$OUT/r02_optimize_H_1000_gpus$g.err
-  tail -1 ../$OUT/r02_optimize_H_1000_gpus$g.err
+  T0=$(date +%s%N)
+  LDPC_GPUS=$g LDPC_OPT_ITERS=$OPT_ITERS LDPC_OPT_SAVE=/tmp/opt_g$g.txt LDPC_OPT_START=data/H05 /tmp/optimize_H > ../$OUT/r02_optimize_H_${OPT_ITERS}_gpus$g.txt 2> ../$OUT/r02_optimize_H_${OPT_ITERS}_gpus$g.err
+  echo "optimize_H LDPC_OPT_ITERS=$OPT_ITERS gpus=$g rc=$? wall $(( ($(date +%s%N) - T0) / 1000000 )) ms (includes the final 10000-frame FER)" | tee -a ../$OUT/r02_optimize_H_timing_n$N.txt
 done
-cmp ../$OUT/r02_optimize_H_1000_gpus1.txt ../$OUT/r02_optimize_H_1000_gpus$N.txt && cmp /tmp/opt_g1.txt /tmp/opt_g$N.txt && echo "optimize_H: identical trajectory and matrix on 1 and $N GPUs"
+cmp ../$OUT/r02_optimize_H_${OPT_ITERS}_gpus1.txt ../$OUT/r02_optimize_H_${OPT_ITERS}_gpus$N.txt && cmp /tmp/opt_g1.txt /tmp/opt_g$N.txt && echo "optimize_H: identical trajectory and matrix on 1 and $N GPUs" | tee -a ../$OUT/r02_optimize_H_timing_n$N.txt
