@@ -617,7 +617,7 @@ def main():
                          "30-50 ms stalls these boxes show now and then (one run in five, whatever samples the clocks) "
                          "stay below a few per cent of the timed region")
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per core of one reference sample")
-    ap.add_argument("--exp-frames", type=int, default=1 << 21,
+    ap.add_argument("--exp-frames", type=int, default=1 << 23,
                     help="total BP frames of the experiment-mode scaling arm on the (3,6)-1008 code (QP-ADMM: 1/16)")
     ap.add_argument("--headline-only", action="store_true", help="only the headline workload (BP on H05)")
     ap.add_argument("--with-experiment", action="store_true",
