@@ -149,7 +149,7 @@ void anneal(Layout &L, int moves) {
 
 template <typename T>
 int upload_vec(T **dst, const std::vector<T> &src) {
-    LDPC_CUDA(cudaMalloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+    LDPC_CUDA(dev_malloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
     if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
     return LDPC_OK;
 }

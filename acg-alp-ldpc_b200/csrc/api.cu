@@ -12,7 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <cstdio>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include "ldpc_internal.h"
@@ -195,7 +197,7 @@ int experiment_enqueue(const ldpc_code *c, const ldpc_algo_cfg_t *cfg, double sn
     job->stream = s.stream;
     job->counters = s.counters;
     if (codeword_source == LDPC_CW_TABLE) {
-        LDPC_CUDA(cudaMalloc((void **) &job->d_words, n_words * (size_t) c->n));
+        LDPC_CUDA(dev_malloc((void **) &job->d_words, n_words * (size_t) c->n));
         LDPC_CUDA(cudaMemcpyAsync(job->d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream));
     }
     LDPC_CUDA(cudaEventCreate(&job->e0));
@@ -227,7 +229,7 @@ void experiment_release(ExperimentJob *job) {
     if (job->stream) { cudaSetDevice(job->device); cudaStreamSynchronize(job->stream); }
     if (job->e0) cudaEventDestroy(job->e0);
     if (job->e1) cudaEventDestroy(job->e1);
-    cudaFree(job->d_words);
+    dev_free(job->d_words);
     cudaGetLastError();
     *job = ExperimentJob();
 }
@@ -378,6 +380,25 @@ Nccl &nccl() {
     return n;
 }
 
+// NCCL prints its version banner to STDOUT at the first communicator when NCCL_DEBUG asks for it (the GPU boxes set it);
+// the drivers' stdout is part of the drop-in surface (main.cpp / optimize_H.cpp / qpadmm_params.cpp print results
+// there), so file descriptor 1 points at stderr while a communicator is being created.
+struct StdoutToStderr {
+    int saved = -1;
+    StdoutToStderr() {
+        fflush(stdout);
+        saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+    }
+    ~StdoutToStderr() {
+        if (saved >= 0) {
+            fflush(stdout);
+            dup2(saved, 1);
+            close(saved);
+        }
+    }
+};
+
 int nccl_fail(ncclResult_t r, const char *what) {
     return fail(LDPC_E_CUDA, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error"));
 }
@@ -435,6 +456,7 @@ int ldpc_experiment_run_multi(const ldpc_code_t *const *codes, int32_t n_devices
         if (it == g_comm_sets.end()) {
             CommSet cs;
             cs.comms.resize(n_devices);
+            StdoutToStderr quiet;
             LDPC_NCCL(nc.CommInitAll(cs.comms.data(), n_devices, devices.data()));
             it = g_comm_sets.emplace(devices, cs).first;
         }
@@ -489,7 +511,11 @@ int ldpc_comm_init(int32_t rank, int32_t world, const uint8_t id[LDPC_COMM_ID_BY
     c->world = world;
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
-    ncclResult_t r = nc.CommInitRank(&c->comm, world, u, rank);
+    ncclResult_t r;
+    {
+        StdoutToStderr quiet;
+        r = nc.CommInitRank(&c->comm, world, u, rank);
+    }
     if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { nc.CommDestroy(c->comm); delete c; return cuda_fail(e, "stream", __FILE__, __LINE__); }
@@ -571,17 +597,17 @@ int ldpc_qpadmm_grid_run(const ldpc_code_t *c, int32_t points, const double *alp
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<unsigned long long> host_cnt(nb * LDPC_CNT_COUNT);
     auto cleanup = [&]() {
-        cudaFree(d_words); cudaFree(d_par); cudaFree(d_cnt);
+        dev_free(d_words); dev_free(d_par); dev_free(d_cnt);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
     cudaError_t e = cudaSuccess;
     if (codeword_source == LDPC_CW_TABLE) {
-        e = cudaMalloc((void **) &d_words, n_words * (size_t) c->n);
+        e = dev_malloc((void **) &d_words, n_words * (size_t) c->n);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void **) &d_par, sizeof(double) * 2 * nb);
-    if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, sizeof(unsigned long long) * nb * LDPC_CNT_COUNT);
+    if (e == cudaSuccess) e = dev_malloc((void **) &d_par, sizeof(double) * 2 * nb);
+    if (e == cudaSuccess) e = dev_malloc((void **) &d_cnt, sizeof(unsigned long long) * nb * LDPC_CNT_COUNT);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, ba.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + nb, bm.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nb * LDPC_CNT_COUNT, s.stream);

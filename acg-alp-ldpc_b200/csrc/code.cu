@@ -30,10 +30,82 @@ int cuda_fail(cudaError_t err, const char *what, const char *file, int line) {
 
 double llr_variance(double snr) { return std::pow(10, -(snr / 10)) / 2; }
 
+// ---- caching pool for device tables (see ldpc_internal.h)
+namespace {
+struct DevPool {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void *>> idle;      // (device, size class) -> blocks
+    std::map<void *, std::pair<int, size_t>> owner;                   // every block handed out or idle
+    std::map<int, size_t> idle_bytes;
+};
+DevPool &dev_pool() {
+    static DevPool *p = new DevPool();        // leaked on purpose: host threads may free blocks while the process exits
+    return *p;
+}
+size_t pool_class(size_t bytes) {             // powers of two from 512 B; above 1 MiB multiples of 1 MiB
+    if (bytes > (1u << 20)) return (bytes + (1u << 20) - 1) & ~(size_t) ((1u << 20) - 1);
+    size_t c = 512;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+}  // namespace
+
+cudaError_t dev_malloc(void **ptr, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t cls = pool_class(std::max<size_t>(bytes, 1));
+    DevPool &P = dev_pool();
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.idle.find({dev, cls});
+        if (it != P.idle.end() && !it->second.empty()) {
+            *ptr = it->second.back();
+            it->second.pop_back();
+            P.idle_bytes[dev] -= cls;
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(ptr, cls);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(P.mu);
+    P.owner[*ptr] = {dev, cls};
+    return cudaSuccess;
+}
+
+void dev_free(void *ptr) {
+    if (!ptr) return;
+    static const size_t cap = [] {
+        const char *e = getenv("LDPC_POOL_CAP_MB");
+        return (size_t) (e ? std::max(0, atoi(e)) : 256) << 20;
+    }();
+    DevPool &P = dev_pool();
+    int dev = -1;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.owner.find(ptr);
+        if (it != P.owner.end()) {
+            dev = it->second.first;
+            const size_t cls = it->second.second;
+            if (P.idle_bytes[dev] + cls <= cap) {
+                P.idle[{dev, cls}].push_back(ptr);
+                P.idle_bytes[dev] += cls;
+                return;
+            }
+            P.owner.erase(it);
+        }
+    }
+    int cur = 0;                              // over the cap (or not ours): really free, on the block's device
+    cudaGetDevice(&cur);
+    if (dev >= 0 && dev != cur) cudaSetDevice(dev);
+    cudaFree(ptr);
+    if (dev >= 0 && dev != cur) cudaSetDevice(cur);
+}
+
 template <typename T>
 static int upload(T **dst, const std::vector<T> &src) {
     size_t bytes = sizeof(T) * std::max<size_t>(src.size(), 1);
-    LDPC_CUDA(cudaMalloc((void **) dst, bytes));
+    LDPC_CUDA(dev_malloc((void **) dst, bytes));
     if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
     return LDPC_OK;
 }
@@ -161,14 +233,14 @@ int ldpc_code_create_dense(int32_t m, int32_t n, const uint8_t *H, int device, l
 void ldpc_code_destroy(ldpc_code_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d.chk_rs); cudaFree(c->d.var_rec); cudaFree(c->d.var_edges);
-    cudaFree(c->d.col_ptr); cudaFree(c->d.row_ptr); cudaFree(c->d.col_idx);
-    cudaFree(c->d.blocks); cudaFree(c->d.admm_var); cudaFree(c->d.admm_inc); cudaFree(c->d.admm_var_id); cudaFree(c->d.admm_var_rank);
-    cudaFree(c->d.gen_cols);
+    dev_free(c->d.chk_rs); dev_free(c->d.var_rec); dev_free(c->d.var_edges);
+    dev_free(c->d.col_ptr); dev_free(c->d.row_ptr); dev_free(c->d.col_idx);
+    dev_free(c->d.blocks); dev_free(c->d.admm_var); dev_free(c->d.admm_inc); dev_free(c->d.admm_var_id); dev_free(c->d.admm_var_rank);
+    dev_free(c->d.gen_cols);
     free_chk_tables(c);
-    for (auto &kv : c->bp_sched) { cudaFree(kv.second.jobs_v); cudaFree(kv.second.jobs_c); }
+    for (auto &kv : c->bp_sched) { dev_free(kv.second.jobs_v); dev_free(kv.second.jobs_c); }
     for (auto &kv : c->bp_lr_sched) {
-        cudaFree(kv.second.rec_v); cudaFree(kv.second.steps); cudaFree(kv.second.var_store);
+        dev_free(kv.second.rec_v); dev_free(kv.second.steps); dev_free(kv.second.var_store);
     }
     delete c;
 }
@@ -193,7 +265,7 @@ int ldpc_code_set_generator(ldpc_code_t *c, int32_t k, const uint8_t *G) {
     for (int i = 0; i < k; ++i)
         for (int j = 0; j < c->n; ++j)
             if (G[(size_t) i * c->n + j]) cols[(size_t) j * kw + i / 32] |= 1u << (i % 32);
-    cudaFree(c->d.gen_cols);
+    dev_free(c->d.gen_cols);
     c->d.gen_cols = nullptr;
     int st = upload(&c->d.gen_cols, cols);
     if (st) return st;

@@ -178,6 +178,14 @@ int measure_smem_peak(int device, double *gbytes_per_s);
 int debug_bpmath(int device, int count, const double *a, const double *ev, const double *od, double *out_exp,
                  double *out_log);
 
+// Device memory of tables and per-call scratch comes from a small caching pool (code.cu): cudaFree synchronises the whole
+// device -- it waits for the kernels of every other host thread -- and cudaMalloc / cudaFree take a process-wide lock, so
+// a host thread that builds and drops a code handle per evaluation (optimize_H.cpp: a new H per proposal, several
+// proposals in flight) would serialise all the others.  Freed blocks are kept per device and size class and handed out
+// again; at most LDPC_POOL_CAP_MB (default 256) of idle blocks are kept per device.
+cudaError_t dev_malloc(void **ptr, size_t bytes);
+void dev_free(void *ptr);
+
 // Opts a kernel into the full dynamic shared memory of an SM (227 KB minus its static share).  The attribute is
 // per-function state shared by every host thread: setting it to the size of ONE launch races with a concurrent launch
 // of another code that needs more (optimize_H.cpp evaluates several H at once) -- "invalid argument" at launch; the

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
 
 template <typename T>
 static int upload_chk(T **dst, const std::vector<T> &src) {
-    LDPC_CUDA(cudaMalloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+    LDPC_CUDA(dev_malloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
     if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
     return LDPC_OK;
 }
@@ -976,7 +976,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
 
 void free_chk_tables(ldpc_code *c) {
     for (AdmmChkTables &t : c->admm_chk) {
-        cudaFree(t.chk_tab); cudaFree(t.var_stream); cudaFree(t.var_rank); cudaFree(t.var_e);
+        dev_free(t.chk_tab); dev_free(t.var_stream); dev_free(t.var_rank); dev_free(t.var_e);
     }
 }
 

@@ -115,22 +115,31 @@ inline int &pinned_gpu() {
 inline ExperimentResult gpu_experiment(const GpuDecoder &decoder, const vector<TCodeword> &codewords, const TMatrix &H,
                                        double snr) {
     const size_t frames = codewords.size(), n = H[0].size();
+    const auto tp = chrono::steady_clock::now();
     vector<uint8_t> words(frames * n);
-    for (size_t f = 0; f < frames; ++f)
-        for (size_t i = 0; i < n; ++i) words[f * n + i] = codewords[f][i];
+    for (size_t f = 0; f < frames; ++f) copy(codewords[f].begin(), codewords[f].end(), words.begin() + f * n);
+    if (getenv("LDPC_EXP_TRACE"))
+        cerr << "gpu_experiment: codeword table " << chrono::duration<double, milli>(chrono::steady_clock::now() - tp).count() << " ms" << endl;
     if (pinned_gpu() >= 0) {
+        const auto t0 = chrono::steady_clock::now();
         CodeRef code = CodeCache::instance().get(H, pinned_gpu());
+        const auto t1 = chrono::steady_clock::now();
         const ldpc_algo_cfg_t cfg1 = decoder.config();
         uint64_t cnt[LDPC_CNT_COUNT];
         double secs = 0;
         if (ldpc_experiment_run(code.get(), &cfg1, snr, experiment_seed(), 0, frames, LDPC_CW_TABLE, words.data(), frames, cnt,
                                 &secs) != LDPC_OK)
             die("ldpc_experiment_run");
+        if (getenv("LDPC_EXP_TRACE"))
+            cerr << "gpu_experiment: code handle " << chrono::duration<double, milli>(t1 - t0).count() << " ms, run "
+                 << chrono::duration<double, milli>(chrono::steady_clock::now() - t1).count() << " ms (kernel " << secs * 1e3
+                 << " ms)" << endl;
         return from_counters(cnt, secs);
     }
     // several GPUs: shards by global frame index, counter blocks all-reduced over NVLink by NCCL inside the library
     // (the reference's merge_exp_results after pthread_join, experiment.h:70-78, 133-137)
-    const int gpus = max(1, min<int>(visible_gpus(), (int) max<size_t>(frames, 1)));
+    // (a GPU is worth a shard of a few thousand frames: the 1000-frame evaluations of optimize_H.cpp stay on one device)
+    const int gpus = max(1, min<int>(visible_gpus(), (int) (frames / 4096)));
     const ldpc_algo_cfg_t cfg = decoder.config();
     vector<CodeRef> codes;
     vector<const ldpc_code_t *> handles;

@@ -27,13 +27,28 @@ const int THREADS_NUM = 200;
 double SNR = -3.0;
 shared_ptr<QPADMMDecoder> decoder = make_shared<QPADMMDecoder>(1.95, 0.5, 1000, 1e-5);
 
+// LDPC_OPT_TRACE=1: where a proposal's time goes (microseconds summed over all evaluations, printed to stderr at exit)
+static atomic<long long> g_us_orth(0), g_us_words(0), g_us_exp(0), g_evals(0);
+static inline long long now_us() {
+    return chrono::duration_cast<chrono::microseconds>(chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // FER of the decoder on `tests_num` codewords of H drawn from mt19937(239); 1.0 when H is rank deficient
 double FER(const TMatrix &H, int tests_num = 1000) {
+    const long long t0 = now_us();
     pair<TMatrix, bool> gen = GetOrtogonal(H);
+    const long long t1 = now_us();
+    g_us_orth += t1 - t0;
+    ++g_evals;
     if (!gen.second) return 1.0;
     mt19937 rnd(239);
     vector<TCodeword> codewords = gen_random_codewords(gen.first, tests_num, rnd);
-    return multithread_experiment(decoder, codewords, H, SNR, THREADS_NUM).FER();
+    const long long t2 = now_us();
+    g_us_words += t2 - t1;
+    const double fer = multithread_experiment(decoder, codewords, H, SNR, THREADS_NUM).FER();
+    g_us_exp += now_us() - t2;
+    if (getenv("LDPC_EXP_TRACE")) cerr << "FER(): multithread_experiment " << (now_us() - t2) / 1000.0 << " ms" << endl;
+    return fer;
 }
 
 // A block matrix whose (i, j) block is either zero or the identity cyclically shifted by diagonals[i][j].
@@ -208,5 +223,9 @@ int main() {
     TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
 
     cout << FER(H, 10000) << endl;
+    if (getenv("LDPC_OPT_TRACE"))
+        cerr << "trace: " << g_evals << " evaluations; per evaluation: GetOrtogonal " << g_us_orth / max(1LL, (long long) g_evals)
+             << " us, codewords " << g_us_words / max(1LL, (long long) g_evals) << " us, experiment (code handle + upload + "
+             << "kernel) " << g_us_exp / max(1LL, (long long) g_evals) << " us; window " << window << endl;
     return 0;
 }
