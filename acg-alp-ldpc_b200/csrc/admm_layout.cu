@@ -147,13 +147,6 @@ void anneal(Layout &L, int moves) {
     }
 }
 
-template <typename T>
-int upload_vec(T **dst, const std::vector<T> &src) {
-    LDPC_CUDA(dev_malloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
-    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
-    return LDPC_OK;
-}
-
 }  // namespace
 
 int compile_admm(ldpc_code *c) {
@@ -278,13 +271,15 @@ int compile_admm(ldpc_code *c) {
         blocks[r] = ab;
     }
     int st;
-    if ((st = upload_vec(&c->d.blocks, blocks))) return st;
-    if ((st = upload_vec(&c->d.admm_var, vrec))) return st;
-    if ((st = upload_vec(&c->d.admm_inc, inc))) return st;
-    if ((st = upload_vec(&c->d.admm_var_id, var_id))) return st;
     std::vector<uint16_t> var_rank(n);
     for (int i = 0; i < n; ++i) var_rank[i] = (uint16_t) L.rank_v[i];
-    if ((st = upload_vec(&c->d.admm_var_rank, var_rank))) return st;
+    TableStager stage;
+    stage.add(&c->d.blocks, blocks);
+    stage.add(&c->d.admm_var, vrec);
+    stage.add(&c->d.admm_inc, inc);
+    stage.add(&c->d.admm_var_id, var_id);
+    stage.add(&c->d.admm_var_rank, var_rank);
+    if ((st = stage.commit(&c->d.blob_admm))) return st;
     return LDPC_OK;
 }
 

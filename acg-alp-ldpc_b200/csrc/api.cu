@@ -32,6 +32,7 @@ struct Slot {
     int32_t *iters = nullptr;
     size_t cap_frames = 0, cap_n = 0;
     bool has_soft = false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;   // timing events of the experiment entry points (created once)
 };
 
 struct ThreadCtx {
@@ -45,6 +46,8 @@ struct ThreadCtx {
                 if (s.stream) cudaStreamSynchronize(s.stream);
                 cudaFree(s.queue); cudaFree(s.counters); cudaFree(s.y); cudaFree(s.soft);
                 cudaFree(s.bits); cudaFree(s.ok); cudaFree(s.iters);
+                if (s.e0) cudaEventDestroy(s.e0);
+                if (s.e1) cudaEventDestroy(s.e1);
                 if (s.stream) cudaStreamDestroy(s.stream);
             }
         }
@@ -200,8 +203,10 @@ int experiment_enqueue(const ldpc_code *c, const ldpc_algo_cfg_t *cfg, double sn
         LDPC_CUDA(dev_malloc((void **) &job->d_words, n_words * (size_t) c->n));
         LDPC_CUDA(cudaMemcpyAsync(job->d_words, words, n_words * (size_t) c->n, cudaMemcpyHostToDevice, s.stream));
     }
-    LDPC_CUDA(cudaEventCreate(&job->e0));
-    LDPC_CUDA(cudaEventCreate(&job->e1));
+    if (!s.e0) LDPC_CUDA(cudaEventCreate(&s.e0));
+    if (!s.e1) LDPC_CUDA(cudaEventCreate(&s.e1));
+    job->e0 = s.e0;
+    job->e1 = s.e1;
     LDPC_CUDA(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * LDPC_CNT_COUNT, s.stream));
     FrameIO io;
     io.experiment = 1; io.seed = seed; io.frame_begin = frame_begin; io.cw_source = codeword_source;
@@ -227,9 +232,7 @@ int experiment_collect(ExperimentJob *job, uint64_t counters[LDPC_CNT_COUNT], do
 
 void experiment_release(ExperimentJob *job) {
     if (job->stream) { cudaSetDevice(job->device); cudaStreamSynchronize(job->stream); }
-    if (job->e0) cudaEventDestroy(job->e0);
-    if (job->e1) cudaEventDestroy(job->e1);
-    dev_free(job->d_words);
+    dev_free(job->d_words);                   // (the events belong to the thread's slot)
     cudaGetLastError();
     *job = ExperimentJob();
 }

@@ -154,12 +154,14 @@ static int compile_bp(ldpc_code *c) {
     std::vector<uint16_t> rowp(c->row_ptr.begin(), c->row_ptr.end());
     std::vector<uint16_t> coli(c->col_idx.begin(), c->col_idx.end());
     int st;
-    if ((st = upload(&c->d.chk_rs, chk_rs))) return st;
-    if ((st = upload(&c->d.var_rec, var_rec))) return st;
-    if ((st = upload(&c->d.var_edges, var_edges))) return st;
-    if ((st = upload(&c->d.col_ptr, colp))) return st;
-    if ((st = upload(&c->d.row_ptr, rowp))) return st;
-    if ((st = upload(&c->d.col_idx, coli))) return st;
+    TableStager stage;
+    stage.add(&c->d.chk_rs, chk_rs);
+    stage.add(&c->d.var_rec, var_rec);
+    stage.add(&c->d.var_edges, var_edges);
+    stage.add(&c->d.col_ptr, colp);
+    stage.add(&c->d.row_ptr, rowp);
+    stage.add(&c->d.col_idx, coli);
+    if ((st = stage.commit(&c->d.blob_bp))) return st;
     return LDPC_OK;
 }
 
@@ -233,9 +235,8 @@ int ldpc_code_create_dense(int32_t m, int32_t n, const uint8_t *H, int device, l
 void ldpc_code_destroy(ldpc_code_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    dev_free(c->d.chk_rs); dev_free(c->d.var_rec); dev_free(c->d.var_edges);
-    dev_free(c->d.col_ptr); dev_free(c->d.row_ptr); dev_free(c->d.col_idx);
-    dev_free(c->d.blocks); dev_free(c->d.admm_var); dev_free(c->d.admm_inc); dev_free(c->d.admm_var_id); dev_free(c->d.admm_var_rank);
+    dev_free(c->d.blob_bp);
+    dev_free(c->d.blob_admm);
     dev_free(c->d.gen_cols);
     free_chk_tables(c);
     for (auto &kv : c->bp_sched) { dev_free(kv.second.jobs_v); dev_free(kv.second.jobs_c); }

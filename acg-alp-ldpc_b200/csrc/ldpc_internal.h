@@ -5,6 +5,8 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -84,6 +86,7 @@ struct AdmmChkTables {
     int special_lo = 0, special_hi = 0;
     int n_chk = 0, n_chunks = 0, n_inc = 0, n_slots = 0, tab_stride = 0, max_nb = 0, e_min = 0;
     int stream_rows = 0;          // rows of var_stream (words per lane column, two rows of padding included)
+    void *blob = nullptr;         // the one device allocation behind the four tables
 };
 
 struct DeviceTables {
@@ -103,6 +106,8 @@ struct DeviceTables {
     uint16_t *admm_var_rank = nullptr; // variable index (< n) -> rank
     // generator (optional): column j of G packed over k bits, k_words words per column
     uint32_t *gen_cols = nullptr;
+    // the device allocations behind the BP and the QP-ADMM tables (one blob each, TableStager)
+    void *blob_bp = nullptr, *blob_admm = nullptr;
 };
 
 }  // namespace ldpc
@@ -186,16 +191,57 @@ int debug_bpmath(int device, int count, const double *a, const double *ev, const
 cudaError_t dev_malloc(void **ptr, size_t bytes);
 void dev_free(void *ptr);
 
+// Several tables, ONE allocation and ONE host-to-device copy: every CUDA runtime call takes a process-wide lock, and
+// with a code handle per proposal and a host thread per GPU (optimize_H.cpp) the ~20 small uploads of a handle were what
+// the evaluation threads queued for.  add() stages a table and remembers where its device pointer goes; commit()
+// allocates the blob (256-byte aligned parts), copies once and sets the pointers.  Only the blob is freed.
+class TableStager {
+public:
+    template <typename T>
+    void add(T **dst, const std::vector<T> &src) {
+        const size_t off = (host_.size() + 255) & ~(size_t) 255;
+        host_.resize(off + std::max<size_t>(sizeof(T) * src.size(), 1));
+        if (!src.empty()) memcpy(host_.data() + off, src.data(), sizeof(T) * src.size());
+        items_.push_back(Item{reinterpret_cast<void **>(dst), off});
+    }
+    int commit(void **blob) {
+        LDPC_CUDA(dev_malloc(blob, std::max<size_t>(host_.size(), 1)));
+        if (!host_.empty()) LDPC_CUDA(cudaMemcpy(*blob, host_.data(), host_.size(), cudaMemcpyHostToDevice));
+        for (const Item &it : items_) *it.dst = static_cast<char *>(*blob) + it.off;
+        return LDPC_OK;
+    }
+
+private:
+    struct Item { void **dst; size_t off; };
+    std::vector<char> host_;
+    std::vector<Item> items_;
+};
+
 // Opts a kernel into the full dynamic shared memory of an SM (227 KB minus its static share).  The attribute is
 // per-function state shared by every host thread: setting it to the size of ONE launch races with a concurrent launch
 // of another code that needs more (optimize_H.cpp evaluates several H at once) -- "invalid argument" at launch; the
 // constant maximum cannot race.
 template <typename Kernel>
 inline cudaError_t allow_max_dynamic_smem(Kernel kernel) {
-    cudaFuncAttributes attr;
-    cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+    // once per (kernel, device): the two runtime calls take the process-wide lock the launches of other threads wait for
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, bool> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int) attr.sharedSizeBytes);
+    const std::pair<const void *, int> key(reinterpret_cast<const void *>(kernel), dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (done.count(key)) return cudaSuccess;
+    }
+    cudaFuncAttributes attr;
+    e = cudaFuncGetAttributes(&attr, kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int) attr.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    done[key] = true;
+    return cudaSuccess;
 }
 
 // sigma^2 exactly as utils/channel.h:12 computes it on the host

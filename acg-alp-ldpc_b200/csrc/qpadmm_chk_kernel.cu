@@ -520,13 +520,6 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
 
 // ---------------------------------------------------------------- host side
 
-template <typename T>
-static int upload_chk(T **dst, const std::vector<T> &src) {
-    LDPC_CUDA(dev_malloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
-    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
-    return LDPC_OK;
-}
-
 // Bank-aware ranks for codes that run one frame per CTA (more than 320 live checks): with F = 1 a warp's gathers go to
 // 32 unrelated addresses -- 43 % of all shared-memory wavefronts of the (3,6)-1008 code were replays
 // (profiles/r01b_admm_chk_1008_ncu.txt).  The order of the checks inside a degree class and of the variables inside
@@ -831,10 +824,12 @@ static int get_chk_tables(const ldpc_code *c, int F, const AdmmChkTables **out) 
                 for (size_t k = 0; k < col_words[col].size(); ++k) stream[k * cols + col] = col_words[col][k];
             t.e_min = e_min;
             int st;
-            if ((st = upload_chk(&t.chk_tab, tab))) return st;
-            if ((st = upload_chk(&t.var_stream, stream))) return st;
-            if ((st = upload_chk(&t.var_rank, vslot))) return st;
-            if ((st = upload_chk(&t.var_e, se))) return st;
+            TableStager stage;
+            stage.add(&t.chk_tab, tab);
+            stage.add(&t.var_stream, stream);
+            stage.add(&t.var_rank, vslot);
+            stage.add(&t.var_e, se);
+            if ((st = stage.commit(&t.blob))) return st;
         }
     }
     *out = &t;
@@ -976,7 +971,7 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
 
 void free_chk_tables(ldpc_code *c) {
     for (AdmmChkTables &t : c->admm_chk) {
-        dev_free(t.chk_tab); dev_free(t.var_stream); dev_free(t.var_rank); dev_free(t.var_e);
+        dev_free(t.blob);
     }
 }
 

@@ -215,14 +215,20 @@ int main() {
     const string save = getenv("LDPC_OPT_SAVE") ? getenv("LDPC_OPT_SAVE") : "data/optimalH.txt";
     PermutationsMatrix H0 = getenv("LDPC_OPT_START") ? PermutationsMatrix(20, load_matrix(getenv("LDPC_OPT_START")))
                                                      : random_permutation_matrix(20, 8, 14);
+    const long long t_start = now_us();
     mt19937 rnd(239);
     // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value)
     // default: two proposals in flight per GPU, so that the host work of one (GetOrtogonal, 1000 codewords, compiling
     // and uploading the new H) overlaps the evaluation of the other
     const int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : 2 * ldpc_host::visible_gpus();
     TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
+    const long long t_search = now_us();
 
     cout << FER(H, 10000) << endl;
+    if (getenv("LDPC_OPT_TRACE"))
+        cerr << "trace: search (initial FER + " << iters << " proposals) " << (t_search - t_start) / 1000 << " ms = "
+             << (double) (t_search - t_start) / 1000.0 / iters << " ms per proposal; final FER on 10000 frames "
+             << (now_us() - t_search) / 1000 << " ms" << endl;
     if (getenv("LDPC_OPT_TRACE"))
         cerr << "trace: " << g_evals << " evaluations; per evaluation: GetOrtogonal " << g_us_orth / max(1LL, (long long) g_evals)
              << " us, codewords " << g_us_words / max(1LL, (long long) g_evals) << " us, experiment (code handle + upload + "
