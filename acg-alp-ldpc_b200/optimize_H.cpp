@@ -28,7 +28,7 @@ double SNR = -3.0;
 shared_ptr<QPADMMDecoder> decoder = make_shared<QPADMMDecoder>(1.95, 0.5, 1000, 1e-5);
 
 // LDPC_OPT_TRACE=1: where a proposal's time goes (microseconds summed over all evaluations, printed to stderr at exit)
-static atomic<long long> g_us_orth(0), g_us_words(0), g_us_exp(0), g_evals(0);
+static atomic<long long> g_us_orth(0), g_us_words(0), g_us_exp(0), g_us_kernel(0), g_evals(0);
 static inline long long now_us() {
     return chrono::duration_cast<chrono::microseconds>(chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -45,8 +45,10 @@ double FER(const TMatrix &H, int tests_num = 1000) {
     vector<TCodeword> codewords = gen_random_codewords(gen.first, tests_num, rnd);
     const long long t2 = now_us();
     g_us_words += t2 - t1;
-    const double fer = multithread_experiment(decoder, codewords, H, SNR, THREADS_NUM).FER();
+    ExperimentResult res = multithread_experiment(decoder, codewords, H, SNR, THREADS_NUM);
+    const double fer = res.FER();
     g_us_exp += now_us() - t2;
+    g_us_kernel += (long long) (res.time_sec * 1e6);
     if (getenv("LDPC_EXP_TRACE")) cerr << "FER(): multithread_experiment " << (now_us() - t2) / 1000.0 << " ms" << endl;
     return fer;
 }
@@ -232,6 +234,7 @@ int main() {
     if (getenv("LDPC_OPT_TRACE"))
         cerr << "trace: " << g_evals << " evaluations; per evaluation: GetOrtogonal " << g_us_orth / max(1LL, (long long) g_evals)
              << " us, codewords " << g_us_words / max(1LL, (long long) g_evals) << " us, experiment (code handle + upload + "
-             << "kernel) " << g_us_exp / max(1LL, (long long) g_evals) << " us; window " << window << endl;
+             << "kernel) " << g_us_exp / max(1LL, (long long) g_evals) << " us, of which the kernel (CUDA events) "
+             << g_us_kernel / max(1LL, (long long) g_evals) << " us; window " << window << endl;
     return 0;
 }
