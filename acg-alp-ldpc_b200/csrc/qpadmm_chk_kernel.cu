@@ -222,9 +222,11 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
             reinterpret_cast<double *>(sm + p.off_inv)[r] = inv_coef(p.mu, p.alpha, (double) p.slot_e[r]);
     for (int a = tid; a < p.stream_rows * (nt / F); a += nt)
         reinterpret_cast<uint32_t *>(sm + p.off_str)[a] = p.var_stream[a];
-    if (tid < F) {                                        // the all-zero chunk
+    if (tid < F) {                                        // the all-zero chunk, the all-zero v slots
         sts_f64x2(sbase + (p.n_chunks * F + tid) * 16, 0.0, 0.0);
         sts_f64x2(sbase + p.off_w23 + (p.n_chunks * F + tid) * 16, 0.0, 0.0);
+        v_gen[(size_t) p.n_slots * F + tid] = 0.0;
+        v_gen[(size_t) (2 * p.n_slots + 1) * F + tid] = 0.0;
     }
     if (tid == 0) {
         L->c.live = L->c.ran = L->c.done[0] = L->c.done[1] = L->c.fresh = 0u;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
     int nb = -2;                                   // degree - 2: -1 / 0 = the one- and two-variable checks
     uint32_t voff[NB + 2], plane_off[NB];
 #pragma unroll
-    for (int j = 0; j < NB + 2; ++j) voff[j] = 0;
+    for (int j = 0; j < NB + 2; ++j) voff[j] = (uint32_t) p.n_slots * (F * 8);      // the all-zero slot
     if (has_chk) nb = (int) p.chk_tab[(size_t) cr * p.tab_stride] - 2;
     // a warp at the boundary of two degree classes whose block counts differ by one runs ONE code path (chk_update,
     // MIXED): the shorter checks keep their last two variables and the chunk of their last block where the longer
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
     // shared-window addresses of this lane's frame column
     const uint32_t a_w01 = sbase + f * 16;                          // + chunk * F * 16 (w23: + off_w23)
     const uint32_t a_v0 = sbase + p.off_v + f * 8;                  // + slot * F * 8   (second buffer: + vbuf)
-    const uint32_t vbuf = (uint32_t) p.n_slots * F * 8;
+    const uint32_t vbuf = (uint32_t) (p.n_slots + 1) * F * 8;       // (one all-zero slot behind each buffer: absent variables read it)
     const uint32_t a_qa = sbase + p.off_qa + f * 8;
     const uint32_t a_invtab = smem_addr(&L->inv_tab[0][0]) + f * 8;
     const uint32_t a_str = sbase + p.off_str + cr * 4;
@@ -286,8 +288,8 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
 
     for (unsigned trip = 0;; ++trip) {
         const uint32_t a_vcur = a_v0 + ((trip & 1) ? vbuf : 0u);
-        double *vcur_gen = v_gen + (size_t) (trip & 1) * p.n_slots * F;
-        const double *vprev_gen = v_gen + (size_t) ((trip & 1) ^ 1) * p.n_slots * F;
+        double *vcur_gen = v_gen + (size_t) (trip & 1) * (p.n_slots + 1) * F;
+        const double *vprev_gen = v_gen + (size_t) ((trip & 1) ^ 1) * (p.n_slots + 1) * F;
         const unsigned live = L->c.live, ran = L->c.ran;
 
         // ---- warp q < F: stop test of slot q after the previous check phase (qp_admm.h:161-163) / out of iterations;
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1
         if (has_chk && ((run >> f) & 1u)) {
             double va[NB + 2];
 #pragma unroll
-            for (int j = 0; j < NB + 2; ++j) va[j] = (j < nb + 2 + (mx >> 1)) ? lds_f64(a_vcur + voff[j]) : 0.0;
+            for (int j = 0; j < NB + 2; ++j) va[j] = lds_f64(a_vcur + voff[j]);       // absent entries: the all-zero slot
 #define LDPC_CHK_CASE(K, MIX)                                                                                     \
     case K:                                                                                                       \
         if (NB >= K)                                                                                              \
@@ -843,7 +845,7 @@ static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F,
     size_t off = 0;
     off += (size_t) (t.n_chunks + 1) * F * 16;           // w01 (+ the all-zero chunk)
     const size_t off_w23 = off; off += (size_t) (t.n_chunks + 1) * F * 16;
-    const size_t off_v = off; off += (size_t) 2 * t.n_slots * F * 8;
+    const size_t off_v = off; off += (size_t) 2 * (t.n_slots + 1) * F * 8;
     const size_t off_qa = off; off += (size_t) t.n_slots * F * 8;
     const size_t off_inv = off; off += two ? 0 : (size_t) t.n_slots * 8;     // two CTAs per SM: inv_coef is looked up by e instead
     const size_t off_red = off; off += (size_t) F * 32 * 8;
