@@ -46,7 +46,7 @@ BP_SNR, BP_ITERS = -5.0, 100
 ADMM_SNR, ADMM_ITERS, ADMM_ALPHA, ADMM_MU = -3.0, 1000, 1.2, 0.55
 # algorithmic fp64 instructions per unit of work (DESIGN.md "rooflines"):
 # BP in the likelihood-ratio domain: per edge and iteration
-BP_FP64_PER_EDGE_ITER = 12.0          # check: 5.3 Pe/Po recurrences + 5 division; variable: 2.7 products + decision
+BP_FP64_PER_EDGE_ITER = 11.0          # check: 5.3 Pe/Po recurrences + 4 division; variable: 2.7 products + decision
 BP_SMEM_BYTES_PER_EDGE_ITER = 32.0    # each message is read and written once per pass (8 B), two passes
 BP_SMEM_BYTES_PER_VAR_ITER = 8.0      # channel likelihood ratio
 # DRAM traffic per frame from the ncu --set full captures of the two kernels (dram__bytes_read.sum + dram__bytes_write.sum
