@@ -194,8 +194,12 @@ __device__ __forceinline__ double chk_special(double v0, double v1, double &yl0,
 
 // TWO: 64 registers per thread, so that two CTAs of up to 512 lanes share an SM (large codes: one frame per CTA fills
 // 342..512 lanes, and at 96 registers a single CTA per SM has nobody to overlap its phases with)
-template <int F, int NB, bool GRID, bool TWO>
-__global__ void __launch_bounds__(TWO ? 512 : (NB <= 6 ? 640 : 320), TWO ? 2 : 1) qpadmm_chk_kernel(const AdmmChkParams p) {
+// SHAPE 2: 80 registers per thread, so that FIVE CTAs of up to 160 lanes (the 160 x 280 codes, one frame each) share an SM
+// instead of four at 96 registers.
+template <int F, int NB, bool GRID, int SHAPE>
+__global__ void __launch_bounds__(SHAPE == 1 ? 512 : (SHAPE == 2 ? 192 : (NB <= 6 ? 640 : 320)), SHAPE == 1 ? 2 : (SHAPE == 2 ? 4 : 1))
+qpadmm_chk_kernel(const AdmmChkParams p) {
+    constexpr bool TWO = SHAPE == 1;
     extern __shared__ __align__(16) double smem[];
     const KernelIO &io = p.io;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -863,22 +867,26 @@ static size_t chk_smem_layout(const ldpc_code *c, const AdmmChkTables &t, int F,
 using ChkKernel = void (*)(const AdmmChkParams);
 
 template <int F, bool GRID>
-static ChkKernel chk_kernel_for(int nb, bool two) {
-    if (two && F == 1) {
-        if (nb <= 2) return qpadmm_chk_kernel<1, 2, GRID, true>;
-        if (nb <= 4) return qpadmm_chk_kernel<1, 4, GRID, true>;
+static ChkKernel chk_kernel_for(int nb, int shape) {
+    if (shape == 1 && F == 1) {
+        if (nb <= 2) return qpadmm_chk_kernel<1, 2, GRID, 1>;
+        if (nb <= 4) return qpadmm_chk_kernel<1, 4, GRID, 1>;
     }
-    if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID, false>;
-    if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID, false>;
-    if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID, false>;
-    if (nb == 6) return qpadmm_chk_kernel<F, 6, GRID, false>;
-    if (nb <= 8) return qpadmm_chk_kernel<F, 8, GRID, false>;
-    return qpadmm_chk_kernel<F, 10, GRID, false>;
+    if (shape == 2 && F == 1) {
+        if (nb <= 4) return qpadmm_chk_kernel<1, 4, GRID, 2>;
+        if (nb == 5) return qpadmm_chk_kernel<1, 5, GRID, 2>;
+    }
+    if (nb <= 2) return qpadmm_chk_kernel<F, 2, GRID, 0>;
+    if (nb <= 4) return qpadmm_chk_kernel<F, 4, GRID, 0>;
+    if (nb == 5) return qpadmm_chk_kernel<F, 5, GRID, 0>;
+    if (nb == 6) return qpadmm_chk_kernel<F, 6, GRID, 0>;
+    if (nb <= 8) return qpadmm_chk_kernel<F, 8, GRID, 0>;
+    return qpadmm_chk_kernel<F, 10, GRID, 0>;
 }
 
-static ChkKernel chk_kernel_for(int F, int nb, bool grid, bool two) {
-    if (grid) return F == 4 ? chk_kernel_for<4, true>(nb, two) : (F == 2 ? chk_kernel_for<2, true>(nb, two) : chk_kernel_for<1, true>(nb, two));
-    return F == 4 ? chk_kernel_for<4, false>(nb, two) : (F == 2 ? chk_kernel_for<2, false>(nb, two) : chk_kernel_for<1, false>(nb, two));
+static ChkKernel chk_kernel_for(int F, int nb, bool grid, int shape) {
+    if (grid) return F == 4 ? chk_kernel_for<4, true>(nb, shape) : (F == 2 ? chk_kernel_for<2, true>(nb, shape) : chk_kernel_for<1, true>(nb, shape));
+    return F == 4 ? chk_kernel_for<4, false>(nb, shape) : (F == 2 ? chk_kernel_for<2, false>(nb, shape) : chk_kernel_for<1, false>(nb, shape));
 }
 
 // smallest 4 x column degree: DecodeQPADMM answers {zeros, false} when e_min * mu <= alpha (qp_admm.h:108-114)
@@ -953,11 +961,15 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
     bool two = F == 1 && threads > 341 && threads <= 512 && t->max_nb <= 4 &&
                2 * chk_smem_layout(c, *t, F, exp_mode, true, nullptr) <= 227 * 1024;
     if (const char *force = getenv("LDPC_ADMM_TWO")) two = two && atoi(force) != 0;
+    // the 160 x 280 codes (one frame per CTA on at most 160 lanes): five CTAs per SM at 80 registers instead of four at 96
+    bool five = !two && F == 1 && threads <= 160 && t->max_nb >= 3 && t->max_nb <= 5 &&
+                5 * chk_smem_layout(c, *t, F, exp_mode, false, nullptr) <= 227 * 1024;
+    if (const char *force = getenv("LDPC_ADMM_FIVE")) five = five && atoi(force) != 0;
     const size_t smem = chk_smem_layout(c, *t, F, exp_mode, two, &p);
     p.var_stream = t->var_stream;
     p.stream_rows = t->stream_rows;
     p.slot_e = t->var_e;
-    ChkKernel fn = chk_kernel_for(F, t->max_nb, grid, two);
+    ChkKernel fn = chk_kernel_for(F, t->max_nb, grid, two ? 1 : (five ? 2 : 0));
     LDPC_CUDA(allow_max_dynamic_smem(fn));
     int per_sm = 0, sms = 0;
     LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
