@@ -962,9 +962,12 @@ int launch_qpadmm_chk(const ldpc_code *c, const FrameIO &fio, int64_t frames, do
                2 * chk_smem_layout(c, *t, F, exp_mode, true, nullptr) <= 227 * 1024;
     if (const char *force = getenv("LDPC_ADMM_TWO")) two = two && atoi(force) != 0;
     // the 160 x 280 codes (one frame per CTA on at most 160 lanes): five CTAs per SM at 80 registers instead of four at 96
-    bool five = !two && F == 1 && threads <= 160 && t->max_nb >= 3 && t->max_nb <= 5 &&
-                5 * chk_smem_layout(c, *t, F, exp_mode, false, nullptr) <= 227 * 1024;
-    if (const char *force = getenv("LDPC_ADMM_FIVE")) five = five && atoi(force) != 0;
+    // is SLOWER (optimalH 120.2 -> 124.6 ms, H05 120.2 -> 126.3 ms per 32768 x 1000 frame-iterations: the shared-memory
+    // pipe is already 77 % busy and the spills add to it), so it is only an experiment knob (LDPC_ADMM_FIVE=1)
+    bool five = false;
+    if (const char *force = getenv("LDPC_ADMM_FIVE"))
+        five = atoi(force) != 0 && !two && F == 1 && threads <= 160 && t->max_nb >= 3 && t->max_nb <= 5 &&
+               5 * chk_smem_layout(c, *t, F, exp_mode, false, nullptr) <= 227 * 1024;
     const size_t smem = chk_smem_layout(c, *t, F, exp_mode, two, &p);
     p.var_stream = t->var_stream;
     p.stream_rows = t->stream_rows;
