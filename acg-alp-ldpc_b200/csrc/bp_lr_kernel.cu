@@ -891,13 +891,13 @@ using LrKernel = void (*)(const BpLrParams);
 template <int F, int MAXT>
 static LrKernel lr_kernel_ft(bool soft) { return soft ? bp_lr_kernel<F, MAXT, true, false> : bp_lr_kernel<F, MAXT, false, false>; }
 
-// register budget by CTA size: 128 / 102 / 85 registers per thread; the generic-degree routines only at 128
+// register budget by CTA size: 128 registers per thread up to 512 threads, 102 up to 640 (the launcher never asks for
+// more); the generic-degree routines only at 128
 template <int F>
 static LrKernel lr_kernel_f(int threads, bool soft, bool wide) {
     if (wide) return soft ? bp_lr_kernel<F, 512, true, true> : bp_lr_kernel<F, 512, false, true>;
     if (threads <= 512) return lr_kernel_ft<F, 512>(soft);
-    if (threads <= 640) return lr_kernel_ft<F, 640>(soft);
-    return lr_kernel_ft<F, 768>(soft);
+    return lr_kernel_ft<F, 640>(soft);
 }
 
 static LrKernel lr_kernel(int F, int threads, bool soft, bool wide) {
