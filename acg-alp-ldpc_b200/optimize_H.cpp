@@ -15,6 +15,10 @@
 #include <thread>
 #include <utility>
 
+#include <cstring>
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include "experiment.h"
 #include "utils/parse_data.h"
 #include "utils/codeword.h"
@@ -153,6 +157,88 @@ private:
     bool stop_ = false;
 };
 
+// Evaluation PROCESSES (several GPUs): worker k is a child process pinned to GPU k % gpus that reads a matrix from a pipe,
+// evaluates its FER and writes the number back.  Threads of one process share the CUDA runtime's process-wide locks, and
+// with a new code handle per proposal the evaluations queue for them (8 GPUs, 16 threads: 2.1 x one GPU); processes do not.
+// The children are forked BEFORE anything touches CUDA in this process (a CUDA context does not survive fork).
+class ProposalProcs {
+public:
+    ProposalProcs(int workers, int gpus) {
+        for (int k = 0; k < workers; ++k) {
+            int to_child[2], from_child[2];
+            if (pipe(to_child) != 0 || pipe(from_child) != 0) { perror("pipe"); exit(1); }
+            const pid_t pid = fork();
+            if (pid < 0) { perror("fork"); exit(1); }
+            if (pid == 0) {
+                for (const Worker &w : workers_) { close(w.wr); close(w.rd); }      // the siblings' ends
+                close(to_child[1]);
+                close(from_child[0]);
+                ldpc_host::pinned_gpu() = k % gpus;
+                serve(to_child[0], from_child[1]);
+                _exit(0);
+            }
+            close(to_child[0]);
+            close(from_child[1]);
+            workers_.push_back(Worker{pid, to_child[1], from_child[0]});
+        }
+    }
+    ~ProposalProcs() {
+        for (const Worker &w : workers_) { close(w.wr); close(w.rd); }
+        for (const Worker &w : workers_) waitpid(w.pid, nullptr, 0);
+    }
+    int size() const { return (int) workers_.size(); }
+    // send matrix H to worker k (FER on tests_num codewords); the answer is read with collect(k)
+    void submit(int k, const TMatrix &H, int tests_num) {
+        vector<unsigned char> msg(12 + H.size() * H[0].size());
+        const int32_t hdr[3] = {(int32_t) H.size(), (int32_t) H[0].size(), tests_num};
+        memcpy(msg.data(), hdr, 12);
+        size_t at = 12;
+        for (const TCodeword &row : H)
+            for (bool bit : row) msg[at++] = bit;
+        write_all(workers_[k].wr, msg.data(), msg.size());
+    }
+    double collect(int k) {
+        double fer = 1.0;
+        read_all(workers_[k].rd, &fer, sizeof(fer));
+        return fer;
+    }
+
+private:
+    struct Worker { pid_t pid; int wr, rd; };
+    vector<Worker> workers_;
+    static void write_all(int fd, const void *buf, size_t n) {
+        const char *p = static_cast<const char *>(buf);
+        while (n) { const ssize_t k = write(fd, p, n); if (k <= 0) { perror("write"); exit(1); } p += k; n -= (size_t) k; }
+    }
+    static bool read_all(int fd, void *buf, size_t n) {
+        char *p = static_cast<char *>(buf);
+        while (n) { const ssize_t k = read(fd, p, n); if (k <= 0) return false; p += k; n -= (size_t) k; }
+        return true;
+    }
+    static void serve(int rd, int wr) {
+        for (;;) {
+            int32_t hdr[3];
+            if (!read_all(rd, hdr, 12)) return;                   // the parent closed the pipe: done
+            vector<unsigned char> bits((size_t) hdr[0] * hdr[1]);
+            if (!read_all(rd, bits.data(), bits.size())) return;
+            TMatrix H(hdr[0], TCodeword(hdr[1]));
+            for (int r = 0; r < hdr[0]; ++r)
+                for (int c = 0; c < hdr[1]; ++c) H[r][c] = bits[(size_t) r * hdr[1] + c] != 0;
+            const double fer = FER(H, hdr[2]);
+            write_all(wr, &fer, sizeof(fer));
+        }
+    }
+};
+
+static ProposalProcs *g_procs = nullptr;      // non-null: evaluations go to the worker processes
+
+// FER through worker 0 when the evaluation processes exist (this process then never touches CUDA), else here
+static double FER_anywhere(const TMatrix &H, int tests_num = 1000) {
+    if (!g_procs) return FER(H, tests_num);
+    g_procs->submit(0, H, tests_num);
+    return g_procs->collect(0);
+}
+
 // The reference's chain (optimize_H.cpp:89-104), evaluated speculatively: the next `window` proposals are all drawn
 // from the CURRENT matrix with the generator states the sequential loop would have, their FERs are evaluated
 // concurrently (one host thread each, dealt round-robin to the visible GPUs), and the first improving one is
@@ -160,9 +246,9 @@ private:
 // The accepted sequence, the printed lines and the saved matrices are those of the sequential loop (window = 1).
 template <typename Gen>
 PermutationsMatrix optimize(PermutationsMatrix H, Gen &rnd, int iters, const string &save_filepath, int window) {
-    double error = FER(H.to_tmatrix());
+    double error = FER_anywhere(H.to_tmatrix());
     cout << "initial FER=" << error << endl;
-    ProposalPool pool(window > 1 ? window : 0, ldpc_host::visible_gpus());
+    ProposalPool pool(!g_procs && window > 1 ? window : 0, g_procs ? 1 : ldpc_host::visible_gpus());
     for (int i = 0; i < iters;) {
         const int w = max(1, min(window, iters - i));
         vector<PermutationsMatrix> candidates;
@@ -173,8 +259,14 @@ PermutationsMatrix optimize(PermutationsMatrix H, Gen &rnd, int iters, const str
             state_after.push_back(draw);
         }
         vector<double> errors(w, 1.0);
-        if (w == 1) errors[0] = FER(candidates[0].to_tmatrix());
-        else pool.run(w, [&](int k) { errors[k] = FER(candidates[k].to_tmatrix()); });
+        if (g_procs) {
+            for (int k = 0; k < w; ++k) g_procs->submit(k, candidates[k].to_tmatrix(), 1000);
+            for (int k = 0; k < w; ++k) errors[k] = g_procs->collect(k);
+        } else if (w == 1) {
+            errors[0] = FER(candidates[0].to_tmatrix());
+        } else {
+            pool.run(w, [&](int k) { errors[k] = FER(candidates[k].to_tmatrix()); });
+        }
         int used = w;
         for (int k = 0; k < w; ++k) {
             cout << "\tproposal: FER=" << errors[k] << endl;
@@ -219,18 +311,45 @@ int main() {
                                                      : random_permutation_matrix(20, 8, 14);
     const long long t_start = now_us();
     mt19937 rnd(239);
-    // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value)
-    // default: two proposals in flight per GPU, so that the host work of one (GetOrtogonal, 1000 codewords, compiling
-    // and uploading the new H) overlaps the evaluation of the other
-    const int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : 2 * ldpc_host::visible_gpus();
+    // Several GPUs: evaluation processes, two per GPU (LDPC_OPT_PROCS overrides; 0 = evaluation threads in this process).
+    // The GPU count is asked for in a short-lived child, so that this process has not touched CUDA when it forks.
+    int gpus = 1;
+    {
+        int fd[2];
+        if (pipe(fd) == 0) {
+            const pid_t pid = fork();
+            if (pid == 0) {
+                const int n = ldpc_host::visible_gpus();
+                if (write(fd[1], &n, sizeof(n)) != (ssize_t) sizeof(n)) _exit(1);
+                _exit(0);
+            }
+            close(fd[1]);
+            if (pid > 0) {
+                if (read(fd[0], &gpus, sizeof(gpus)) != (ssize_t) sizeof(gpus)) gpus = 1;
+                waitpid(pid, nullptr, 0);
+            }
+            close(fd[0]);
+        }
+    }
+    const int procs = getenv("LDPC_OPT_PROCS") ? max(0, atoi(getenv("LDPC_OPT_PROCS"))) : (gpus > 1 ? 2 * gpus : 0);
+    // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value);
+    // default: two in flight per GPU, so that the host work of one (GetOrtogonal, 1000 codewords, compiling and
+    // uploading the new H) overlaps the evaluation of the other
+    int window = getenv("LDPC_OPT_WINDOW") ? max(1, atoi(getenv("LDPC_OPT_WINDOW"))) : 2 * gpus;
+    ProposalProcs *procs_owner = nullptr;
+    if (procs > 0) {
+        g_procs = procs_owner = new ProposalProcs(procs, gpus);
+        window = min(window, procs);
+    }
     TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
     const long long t_search = now_us();
 
-    cout << FER(H, 10000) << endl;
+    cout << FER_anywhere(H, 10000) << endl;
     if (getenv("LDPC_OPT_TRACE"))
         cerr << "trace: search (initial FER + " << iters << " proposals) " << (t_search - t_start) / 1000 << " ms = "
              << (double) (t_search - t_start) / 1000.0 / iters << " ms per proposal; final FER on 10000 frames "
-             << (now_us() - t_search) / 1000 << " ms" << endl;
+             << (now_us() - t_search) / 1000 << " ms; evaluation processes " << procs << ", window " << window << endl;
+    delete procs_owner;
     if (getenv("LDPC_OPT_TRACE"))
         cerr << "trace: " << g_evals << " evaluations; per evaluation: GetOrtogonal " << g_us_orth / max(1LL, (long long) g_evals)
              << " us, codewords " << g_us_words / max(1LL, (long long) g_evals) << " us, experiment (code handle + upload + "

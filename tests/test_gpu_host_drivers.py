@@ -176,18 +176,20 @@ def test_qpadmm_params_grid_equals_oracle(work, helper, oracle):
 
 def test_optimize_H_trajectory_is_window_invariant(work):
     """optimize_H.cpp: the speculative window (proposals evaluated concurrently, generator rewound on accept) must not
-    change the chain: stdout and every saved matrix are byte-identical for windows 1, 3 and 8."""
+    change the chain: stdout and every saved matrix are byte-identical for windows 1, 3 and 8 -- with evaluation threads
+    and with evaluation processes (the multi-GPU mode, forced here on one GPU)."""
     exe = _build(work, os.path.join(PKG, "optimize_H.cpp"), "optimize_H")
     outs, mats = [], []
-    for window in (1, 3, 8):
-        save = str(work / ("opt_w%d.txt" % window))
+    for window, procs in ((1, 0), (3, 0), (8, 0), (4, 4), (2, 5)):
+        save = str(work / ("opt_w%d_p%d.txt" % (window, procs)))
         run = subprocess.run([exe], cwd=work, capture_output=True, text=True,
-                             env=_env(LDPC_OPT_ITERS=40, LDPC_OPT_WINDOW=window, LDPC_OPT_SAVE=save, LDPC_OPT_START="data/H05"))
+                             env=_env(LDPC_OPT_ITERS=40, LDPC_OPT_WINDOW=window, LDPC_OPT_PROCS=procs, LDPC_OPT_SAVE=save,
+                                      LDPC_OPT_START="data/H05"))
         assert run.returncode == 0, run.stderr[-2000:]
         outs.append(run.stdout)
         mats.append(open(save).read() if os.path.exists(save) else "")
-    assert outs[0] == outs[1] == outs[2]
-    assert mats[0] == mats[1] == mats[2]
+    assert all(o == outs[0] for o in outs)
+    assert all(m == mats[0] for m in mats)
     lines = outs[0].splitlines()
     assert lines[0].startswith("initial FER=") and sum(l.startswith("\tproposal: FER=") for l in lines) == 40
     assert any(l.startswith("accept, FER=") for l in lines), "no proposal was accepted: the rewind path was not exercised"
