@@ -162,6 +162,29 @@ private:
     bool stop_ = false;
 };
 
+// CUDA start-up grows with the number of visible GPUs (14 s for the first call on an 8 x B200 box against 1.5-4.5 s with one
+// GPU visible), so a process that will use `count` GPUs starting at position `first` of the visible ones narrows
+// CUDA_VISIBLE_DEVICES to them BEFORE it touches CUDA.  (This is the application, not the library: the library never
+// changes the environment.)
+static void narrow_visible_gpus(int first, int count) {
+    vector<string> ids;
+    if (const char *cur = getenv("CUDA_VISIBLE_DEVICES")) {
+        string item;
+        for (const char *c = cur;; ++c) {
+            if (*c == ',' || *c == 0) { if (!item.empty()) ids.push_back(item); item.clear(); if (*c == 0) break; }
+            else item.push_back(*c);
+        }
+    }
+    string value;
+    for (int k = 0; k < count; ++k) {
+        const int pos = first + k;
+        const string id = pos < (int) ids.size() ? ids[pos] : (ids.empty() ? to_string(pos) : string());
+        if (id.empty()) break;
+        value += (value.empty() ? "" : ",") + id;
+    }
+    if (!value.empty()) setenv("CUDA_VISIBLE_DEVICES", value.c_str(), 1);
+}
+
 // Evaluation PROCESSES (several GPUs): worker k is a child process pinned to GPU k % gpus that reads a matrix from a pipe,
 // evaluates its FER and writes the number back.  Threads of one process share the CUDA runtime's process-wide locks, and
 // with a new code handle per proposal the evaluations queue for them (8 GPUs, 16 threads: 2.1 x one GPU); processes do not.
@@ -178,7 +201,8 @@ public:
                 for (const Worker &w : workers_) { close(w.wr); close(w.rd); }      // the siblings' ends
                 close(to_child[1]);
                 close(from_child[0]);
-                ldpc_host::pinned_gpu() = k % gpus;
+                narrow_visible_gpus(k % gpus, 1);              // this process sees ONE GPU, as device 0
+                ldpc_host::pinned_gpu() = 0;
                 serve(to_child[0], from_child[1]);
                 _exit(0);
             }
@@ -354,6 +378,8 @@ int main() {
     if (procs > 0) {
         g_procs = procs_owner = new ProposalProcs(procs, gpus);
         window = min(window, procs);
+    } else {
+        narrow_visible_gpus(0, gpus);                  // evaluation threads in this process: the GPUs it will use
     }
     TMatrix H = optimize(H0, rnd, iters, save, window).to_tmatrix();
     const long long t_search = now_us();
