@@ -295,8 +295,8 @@ static int get_schedule(const ldpc_code *c, int F, int nwarps, BpSchedule *out) 
         std::vector<BpJob> jc = make_jobs(c->chk_classes, F, nwarps, &s.rounds_c);
         LDPC_CUDA(dev_malloc((void **) &s.jobs_v, sizeof(BpJob) * std::max<size_t>(jv.size(), 1)));
         LDPC_CUDA(dev_malloc((void **) &s.jobs_c, sizeof(BpJob) * std::max<size_t>(jc.size(), 1)));
-        LDPC_CUDA(cudaMemcpy(s.jobs_v, jv.data(), sizeof(BpJob) * jv.size(), cudaMemcpyHostToDevice));
-        LDPC_CUDA(cudaMemcpy(s.jobs_c, jc.data(), sizeof(BpJob) * jc.size(), cudaMemcpyHostToDevice));
+        LDPC_CUDA(upload_sync(s.jobs_v, jv.data(), sizeof(BpJob) * jv.size()));
+        LDPC_CUDA(upload_sync(s.jobs_c, jc.data(), sizeof(BpJob) * jc.size()));
         it = c->bp_sched.emplace(std::make_pair(F, nwarps), s).first;
     }
     *out = it->second;

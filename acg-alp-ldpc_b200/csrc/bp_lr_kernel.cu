@@ -532,7 +532,7 @@ static std::vector<uint32_t> deal_steps(const std::vector<BpClass> &classes, int
 template <typename T>
 static int upload_vec(T **dst, const std::vector<T> &src) {
     LDPC_CUDA(dev_malloc((void **) dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
-    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    if (!src.empty()) LDPC_CUDA(upload_sync(*dst, src.data(), sizeof(T) * src.size()));
     return LDPC_OK;
 }
 

@@ -106,7 +106,7 @@ template <typename T>
 static int upload(T **dst, const std::vector<T> &src) {
     size_t bytes = sizeof(T) * std::max<size_t>(src.size(), 1);
     LDPC_CUDA(dev_malloc((void **) dst, bytes));
-    if (!src.empty()) LDPC_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    if (!src.empty()) LDPC_CUDA(upload_sync(*dst, src.data(), sizeof(T) * src.size()));
     return LDPC_OK;
 }
 

@@ -191,6 +191,17 @@ int debug_bpmath(int device, int count, const double *a, const double *ev, const
 cudaError_t dev_malloc(void **ptr, size_t bytes);
 void dev_free(void *ptr);
 
+// Host-to-device upload of a table that a kernel on ANOTHER (non-blocking) stream will read.  cudaMemcpy from pageable
+// memory returns once the source has been staged -- the DMA to the device may still be in flight on the legacy stream,
+// and a kernel launched on a non-blocking stream does not wait for it.  (Seen once in 9000 evaluations of optimize_H
+// with two processes per GPU: a whole evaluation ran on a partly uploaded table blob.)  So: copy on the calling thread's
+// own stream and wait for THAT stream -- complete on return, and no other thread's kernels are waited for.
+inline cudaError_t upload_sync(void *dst, const void *src, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cudaStreamPerThread);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamPerThread);
+}
+
 // Several tables, ONE allocation and ONE host-to-device copy: every CUDA runtime call takes a process-wide lock, and
 // with a code handle per proposal and a host thread per GPU (optimize_H.cpp) the ~20 small uploads of a handle were what
 // the evaluation threads queued for.  add() stages a table and remembers where its device pointer goes; commit()
@@ -206,7 +217,7 @@ public:
     }
     int commit(void **blob) {
         LDPC_CUDA(dev_malloc(blob, std::max<size_t>(host_.size(), 1)));
-        if (!host_.empty()) LDPC_CUDA(cudaMemcpy(*blob, host_.data(), host_.size(), cudaMemcpyHostToDevice));
+        if (!host_.empty()) LDPC_CUDA(upload_sync(*blob, host_.data(), host_.size()));
         for (const Item &it : items_) *it.dst = static_cast<char *>(*blob) + it.off;
         return LDPC_OK;
     }

@@ -7,7 +7,8 @@
 //
 // Environment: LDPC_OPT_ITERS (default 10000), LDPC_OPT_SAVE (default data/optimalH.txt), LDPC_OPT_WINDOW (proposals
 //              evaluated speculatively at once, default = twice the number of GPUs; the trajectory does not depend on it),
-//              LDPC_OPT_START (a matrix stem to start from instead of a random one).
+//              LDPC_OPT_START (a matrix stem to start from instead of a random one), LDPC_OPT_PROCS (evaluation processes
+//              instead of threads), LDPC_OPT_TRACE / LDPC_OPT_TIMELINE (where the time goes, stderr).
 #include <memory>
 #include <mutex>
 #include <functional>
@@ -349,7 +350,7 @@ int main() {
                                                      : random_permutation_matrix(20, 8, 14);
     const long long t_start = now_us();
     mt19937 rnd(239);
-    // Several GPUs: evaluation processes, two per GPU (LDPC_OPT_PROCS overrides; 0 = evaluation threads in this process).
+    // LDPC_OPT_PROCS=<n>: n evaluation processes instead of evaluation threads in this process.
     // The GPU count is asked for in a short-lived child, so that this process has not touched CUDA when it forks.
     int gpus = 1;
     {
@@ -369,7 +370,10 @@ int main() {
             close(fd[0]);
         }
     }
-    const int procs = getenv("LDPC_OPT_PROCS") ? max(0, atoi(getenv("LDPC_OPT_PROCS"))) : (gpus > 1 ? 2 * gpus : 0);
+    // Measured on 8 x B200, 3000 proposals (profiles/r02_optimize_H_8gpu.txt): evaluation threads 0.97 ms per proposal after
+    // 13 s of CUDA start-up, 16 evaluation processes 0.69 ms after 21 s (one GPU: 4.33 ms after 8.6 s) -- the processes
+    // pay off beyond ~28000 proposals, so threads are the default and LDPC_OPT_PROCS=<n> asks for processes.
+    const int procs = getenv("LDPC_OPT_PROCS") ? max(0, atoi(getenv("LDPC_OPT_PROCS"))) : 0;
     // proposals evaluated concurrently (1 = the reference's sequential loop; the trajectory is the same for any value);
     // default: two in flight per GPU, so that the host work of one (GetOrtogonal, 1000 codewords, compiling and
     // uploading the new H) overlaps the evaluation of the other
