@@ -58,3 +58,16 @@ def test_argument_validation(cdll):
     assert cdll.ldpc_code_create(1, 4, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), 0,
                                  C.byref(handle)) == -1
     assert cdll.ldpc_bp_decode(None, None, 0, C.c_double(0), 1, 1, None, None, None, None) == -1
+
+
+def test_multi_gpu_entry_points_validate_and_fail_loudly(cdll):
+    """ldpc_experiment_run_multi / ldpc_comm_*: argument checks, and no silent success without a GPU"""
+    import torch
+    assert cdll.ldpc_experiment_run_multi(None, 0, None, C.c_double(0), 0, 0, 0, 0, None, 0, None, None) == -1
+    assert cdll.ldpc_comm_init(0, 0, None, 0, None) == -1
+    assert cdll.ldpc_allreduce_counters(None, None, 0) == -1
+    cdll.ldpc_comm_destroy(None)                                   # a no-op
+    if not torch.cuda.is_available():
+        comm = C.c_void_p()
+        ident = (C.c_uint8 * 128)()
+        assert cdll.ldpc_comm_init(0, 1, ident, 0, C.byref(comm)) in (-2, -4) and not comm.value   # LDPC_E_CUDA / no NCCL
