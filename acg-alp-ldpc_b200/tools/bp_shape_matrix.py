@@ -1,3 +1,8 @@
+"""Every launch shape of the likelihood-ratio BP kernel (frames per team x teams per CTA x soft output) against the
+log-domain kernel on the same channel samples: flags, bits and iteration counts must be identical.
+
+    python acg-alp-ldpc_b200/tools/bp_shape_matrix.py      (on the GPU box; prints one line per shape)
+"""
 import os, sys, numpy as np
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/acg-alp-ldpc_b200')
 import ldpc_b200 as L
