@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldpc_b200.so")
 SOURCES = ["code.cu", "admm_layout.cu", "api.cu", "bp_kernel.cu", "bp_lr_kernel.cu", "qpadmm_kernel.cu", "qpadmm_chk_kernel.cu", "channel_kernel.cu"]
-HEADERS = ["ldpc_internal.h", "frame.cuh", "channel.cuh", "slots.cuh", "slots_multi.cuh", "slots_team.cuh", "bpmath.cuh", "admm_rows.cuh", "smem_ptx.cuh", os.path.join(ROOT, "include", "ldpc_b200.h")]
+HEADERS = ["ldpc_internal.h", "frame.cuh", "channel.cuh", "slots.cuh", "slots_team.cuh", "bpmath.cuh", "admm_rows.cuh", "smem_ptx.cuh", os.path.join(ROOT, "include", "ldpc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

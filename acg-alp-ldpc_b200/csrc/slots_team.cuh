@@ -1,13 +1,18 @@
 // Frame slots for a TEAM of warps inside a CTA (the likelihood-ratio BP kernel runs several independent teams per
 // CTA, each with its own frames, behind its own named barrier, so that the read-only tables are held once per SM and
-// no team ever waits for another).  Same arithmetic and the same per-frame results as slots.cuh / slots_multi.cuh,
-// with (threadIdx.x, blockDim.x, __syncthreads) replaced by (team.tid, team.nt, team.sync).
+// no team ever waits for another).  Same arithmetic and the same per-frame results as the per-slot versions of
+// slots.cuh, with (threadIdx.x, blockDim.x, __syncthreads) replaced by (team.tid, team.nt, team.sync), and ALL the frames
+// of a slot mask loaded / published in one pass (the per-slot versions cost two to three barriers per frame, which
+// dominates when frames finish after three or four iterations -- SNR >= -1 dB).
 #ifndef LDPC_B200_SLOTS_TEAM_CUH
 #define LDPC_B200_SLOTS_TEAM_CUH
 
-#include "slots_multi.cuh"
+#include "slots.cuh"
 
 namespace ldpc {
+
+// slot index of the k-th set bit of mask (k < popc(mask))
+__device__ __forceinline__ int nth_slot(unsigned mask, int k) { return (int) __fns(mask, 0, k + 1); }
 
 struct Team {
     int tid, nt;        // thread index inside the team, threads of the team (a multiple of 32)
@@ -21,7 +26,9 @@ __device__ __forceinline__ void team_slots_init(const Team &t, SlotBlock<F> *S) 
     if (t.tid < LDPC_CNT_COUNT) S->cnt[t.tid] = 0ull;
 }
 
-// slots_load_all for a team.  Ends with a team barrier.
+// LLRs (2 y / sigma^2, utils/channel.h:14-16) of the frames entering the slots of `mask`; experiment mode also produces
+// the transmitted codewords cw[f * n + i] and the channel Hamming counts.  per_var(i, f, llr) initialises the kernel's
+// per-variable state.  Ends with a team barrier.
 template <int F, typename PerVar>
 __device__ __forceinline__ void team_slots_load_all(const Team &t, const KernelIO &io, SlotBlock<F> *S, unsigned mask,
                                                     uint8_t *cw, PerVar per_var) {
@@ -84,7 +91,8 @@ __device__ __forceinline__ void team_slots_load_all(const Team &t, const KernelI
     t.sync();
 }
 
-// slots_finish_all for a team.  All threads of the team call with identical arguments.
+// Publish the frames of `mask`.  okmask: decoder flags (BP: also "has bits" and "is a codeword").  hard(i, f) /
+// soft(i, f): decision and soft output of variable i of slot f.  All threads of the team call with identical arguments.
 template <int F, typename Hard, typename Soft>
 __device__ __forceinline__ void team_slots_finish_all(const Team &t, const KernelIO &io, SlotBlock<F> *S, unsigned mask,
                                                       unsigned okmask, const uint8_t *cw, Hard hard, Soft soft) {
