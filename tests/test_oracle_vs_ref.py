@@ -74,3 +74,23 @@ def test_admm_problem_shape(oracle):
         assert (p["n_var"], p["R"], p["nnz"]) == (n_var, R, nnz)
         assert R == 4 * T
         assert p["e"].min() == (8 if name == "reg_3_6_1008" else 4)
+
+
+@pytest.mark.parametrize("name,alpha,mu", [("optimalH", 1.2, 0.55), ("H05", 1.95, 0.5), ("reg_3_6_1008", 1.2, 0.55)])
+def test_decoders_at_high_snr_and_on_the_large_code(oracle, ref, name, alpha, mu):
+    """The oracle is also pinned where the GPU parity tests of round 2 reach: +2 / +4 / +6 dB (where the reference's
+    phi form saturates, bp.h:34) and the (3,6)-1008 code, on the reference's own mt19937 channel words."""
+    H = load_rows(name)
+    m, n = H.shape
+    csr = dense_to_csr(H)
+    frames = 24 if name != "reg_3_6_1008" else 6
+    rng = np.random.default_rng(11)
+    for snr in ((2.0, 4.0, 6.0) if name != "reg_3_6_1008" else (-1.0, 2.0)):
+        cw = np.zeros((frames, n), np.uint8)
+        y = np.stack([ref.transmit(snr, cw[i], 5000 + i) for i in range(frames)])
+        rb, rok, _ = ref.bp_decode(H, y, snr, 100)
+        ob, ook, oit, opost = oracle.bp_decode(csr, m, n, y, snr, 100)
+        assert (rok == ook).all() and (rb == ob).all()
+        rb, rok, _ = ref.qpadmm_decode(H, y, snr, alpha, mu, 1000, 1e-5)
+        ob, ook, _, _ = oracle.qpadmm_decode(csr, m, n, y, snr, alpha, mu, 1000, 1e-5)
+        assert (rok == ook).all() and (rb == ob).all()
