@@ -105,3 +105,26 @@ def test_generator_fixture_and_info_bits(oracle):
     c = oracle.encode(G, u)
     assert (c == (u.astype(int) @ G.astype(int)) % 2).all()
     assert 20 < u.sum() < 100
+
+
+def test_oracle_posterior_against_60_digit_arithmetic(oracle):
+    """the fp80 oracle's posterior LLRs (the reference's VNode::estimate, bp.h:85-90, instrumented) against 60-digit
+    arithmetic running the reference's flooding schedule for the same number of iterations: within 1e-4 relative --
+    the yardstick the GPU posterior tests use is itself pinned"""
+    import mpmath as mp
+    from oracle.oracle import dense_to_csr
+    from tests.helpers import load_rows
+    from tests.posterior_accuracy import mp_bp
+    mp.mp.dps = 60
+    H = load_rows("optimalH")
+    m, n = H.shape
+    for snr, frames in ((-1.0, 2), (3.0, 1)):
+        y = oracle.channel(239239239, 41000, frames, n, snr)
+        bits, ok, iters, post = oracle.bp_decode(dense_to_csr(H), m, n, y, snr, 100)
+        assert (ok == 1).all()
+        for f in range(frames):
+            truth = np.array([float(t) for t in mp_bp(H, y[f], snr, int(iters[f]), mp)])
+            fin = np.isfinite(post[f])
+            assert fin.mean() > 0.9
+            assert np.max(np.abs(post[f][fin] - truth[fin]) / np.abs(truth[fin])) < 1e-4
+            assert ((truth <= 0) == (bits[f] == 1)).all()
